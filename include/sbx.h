@@ -1,0 +1,143 @@
+/* sbx.h -- C ABI of the B200-native shaderbox pixel path.
+ *
+ * What this boundary replaces.  shaderbox has no FFI: its boundary is a SOURCE-level plugin
+ * contract.  An app header (src/app_*.h) defines setup_camera / setup_scene / render / FOV and
+ * then includes src/main.h, which supplies
+ *
+ *     void mainImage(out vec4 fragColor, in vec2 fragCoord)            (src/main.h:6-53)
+ *
+ * and a HOST calls that once per pixel after providing the uniforms u_res / u_time / u_mouse
+ * (src/uniform_buffer.h:26-36) plus the optional aux block (src/uniform_buffer.h:39-60).
+ * The hosts in the reference are VML's SDL_app.cpp (C++ CPU; src/Makefile:21, not in the tree),
+ * util/hlsltoy (D3D11; util/hlsltoy/src/hlsltoy.cpp:382-426 compiles the shader at run time and
+ * uploads the two cbuffers) and shadertoy.com.  This library IS such a host: the per-pixel loop
+ * becomes one CUDA grid launch on sm_100a, and the frame is written as raw RGBA32F.
+ *
+ * Conventions
+ *   - every entry point returns 0 (SBX_OK) or a negative sbx_status; no exceptions cross the ABI
+ *   - frames are row-major float4 (R,G,B,A=1), row 0 is fragCoord.y = 0.5 (GL / shadertoy
+ *     bottom-up convention, src/main.h:12), pixel centre fragCoord = (x+0.5, y+0.5)
+ *   - a context is bound to ONE device; calls on one context are serialised by the caller
+ *   - there is NO CPU path: if no sm_100-class device / kernel image is available the calls fail
+ */
+#ifndef SBX_H_
+#define SBX_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sbx_status {
+    SBX_OK = 0,
+    SBX_ERR_INVALID = -1,      /* bad argument (null pointer, non-positive size, bad shard) */
+    SBX_ERR_NO_DEVICE = -2,    /* no usable CUDA device / driver */
+    SBX_ERR_UNKNOWN_APP = -3,  /* app name not registered / not loaded */
+    SBX_ERR_CUDA = -4,         /* a CUDA runtime / driver call failed (see sbx_last_error) */
+    SBX_ERR_COMPILE = -5,      /* run-time compilation of an app header failed (log in sbx_last_error) */
+    SBX_ERR_NOMEM = -6,
+    SBX_ERR_UNSUPPORTED = -7
+} sbx_status;
+
+/* The uniform block.  Field names, meaning and defaults follow src/uniform_buffer.h:
+ *   main block  :26-30 (u_res is width/height below, u_mouse, u_time)
+ *   APP_CLOUDS  :41-54 ; APP_SDF_AO :57-58
+ * u_mouse is the shadertoy iMouse vec4 (src/uniform_buffer.h:35). */
+typedef struct sbx_params {
+    int   width, height;          /* u_res */
+    float u_time;
+    float u_mouse[4];
+    /* aux_uniform_buffer_t, APP_CLOUDS */
+    float wind_dir[3];
+    float sun_dir[3];
+    float sun_color[3];
+    float sun_power;
+    int   cld_march_steps;
+    int   illum_march_steps;
+    float sigma_scattering;
+    float cld_coverage;
+    float cld_thick;
+    float atm_radius;
+    float atm_ground_y;
+    /* aux_uniform_buffer_t, APP_SDF_AO */
+    float fog_density;
+    float fog_falloff;
+} sbx_params;
+
+/* Which rows of the frame a call renders.  The frame is cut into stripes of `stripe_rows`
+ * consecutive rows; stripe s belongs to part (s % n_parts).  A call renders the stripes of `part`
+ * and stores them COMPACTED (in increasing row order) so each part's output is one contiguous
+ * message for the gather.  {1,1,0} (or a zeroed struct) = the whole frame. */
+typedef struct sbx_shard {
+    int stripe_rows;
+    int n_parts;
+    int part;
+} sbx_shard;
+
+typedef struct sbx_timing {
+    float kernel_ms;     /* device time of the last render kernel (CUDA events on its stream) */
+    float h2d_ms;        /* uniform / table upload, if any */
+    float d2h_ms;        /* frame read-back, if the call had a host destination */
+    int   launches;      /* kernels launched by the last call */
+    int   grid_blocks, block_threads, regs_per_thread, blocks_per_sm;
+} sbx_timing;
+
+typedef struct sbx_ctx sbx_ctx;
+
+/* Fill *p with the reference defaults (src/uniform_buffer.h:41-58), width x height, u_time = 0. */
+int sbx_default_params(sbx_params* p, int width, int height);
+
+/* Create a context on CUDA device `device` (primary context; interoperates with torch). */
+int sbx_create(int device, sbx_ctx** out);
+void sbx_destroy(sbx_ctx* ctx);
+
+/* Select the app, by its reference define: "APP_EGG", "APP_CLOUDS", "APP_ATMOSPHERE",
+ * "APP_PLANET", "APP_RAYTRACER" (src/Makefile:9 `APP = -DAPP_PLANET`).  `variant` picks the
+ * implementation: "native" = the hand-written sm_100a kernel built into this library,
+ * "plugin" = the kernel image compiled from an UNCHANGED shaderbox app header (see
+ * sbx_compile_app / the prebuilt images next to the library), NULL = native if present. */
+int sbx_load_app(sbx_ctx* ctx, const char* app_name, const char* variant);
+
+/* Compile an unchanged shaderbox app header (a file that ends in `#include "main.h"`) against the
+ * device operator library with NVRTC for sm_100a, register it under `app_name`, and (if
+ * `image_out_path` is not NULL) also write the cubin there.  The equivalent of hlsltoy's
+ * D3DCompileFromFile (util/hlsltoy/src/hlsltoy.cpp:382-388).  Needs no GPU. */
+int sbx_compile_app(sbx_ctx* ctx_or_null, const char* app_header_path, const char* app_name,
+                    const char* image_out_path);
+
+/* Number of rows / bytes a shard produces for a frame of `height` rows. */
+int sbx_shard_rows(const sbx_shard* shard, int height);
+
+/* Render into DEVICE memory (dev_rgba: rows*width float4, 16-byte aligned) on `stream`
+ * (a cudaStream_t passed as void*, NULL = the legacy default stream).  Asynchronous. */
+int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
+                      float* dev_rgba, void* stream);
+
+/* Render and copy to HOST memory (host_rgba: rows*width*4 floats).  Synchronous; this is the call
+ * the reference-facing hosts make (one frame in, one frame out). */
+int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
+                    float* host_rgba);
+
+/* Scatter a compacted shard (as produced above / received from a peer) into a full frame on the
+ * device: the de-interleave step after the multi-GPU gather. */
+int sbx_unshard_device(sbx_ctx* ctx, int width, int height, const sbx_shard* shard,
+                       const float* dev_part, float* dev_frame, void* stream);
+
+/* Kernel-launch tuning knobs (0 = library default): pixels tile w/h per warp, hash-table size. */
+int sbx_set_option(sbx_ctx* ctx, const char* key, int value);
+
+int sbx_last_timing(sbx_ctx* ctx, sbx_timing* out);
+const char* sbx_last_error(sbx_ctx* ctx_or_null);
+const char* sbx_strerror(int status);
+const char* sbx_version(void);
+
+/* Operator known-answer entry: evaluate one operator of the device library (sdf.h / noise_*.h /
+ * fbm.h / volumetric.h / light.h ... ) on n inputs ON THE DEVICE.  `op` names the operator
+ * ("noise_iq", "hash", "sd_torus", "sinf", ...); in/out are host arrays of n*in_stride /
+ * n*out_stride floats.  Test hook for the operator surface, not a production path. */
+int sbx_eval_op(sbx_ctx* ctx, const char* op, const float* in, int in_stride,
+                float* out, int out_stride, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBX_H_ */

@@ -1,0 +1,66 @@
+"""Loader for the CPU checkers (TEST INFRASTRUCTURE).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (shaderbox_b200) never does.
+
+  oracle/_ref/libsbx_ref.so  -- the reference's own headers compiled on oracle/ref/glsl_shim.h
+                                (built by `make -C oracle ref` where /root/reference exists)
+  oracle/liboracle.so        -- the plain-C restatement oracle/sbx_oracle.c
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from shaderbox_b200.abi import Params, Shard, shard_rows
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libsbx_ref.so")
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+
+_cache = {}
+
+
+def _load(path):
+    if path not in _cache:
+        _cache[path] = C.CDLL(path)
+    return _cache[path]
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def have_oracle():
+    return os.path.exists(ORACLE_SO)
+
+
+def _render(lib, prefix, app, params, shard=None, nthreads=0, want_counts=False):
+    name = app.lower().replace("app_", "")
+    fn = getattr(lib, "%s_render_%s" % (prefix, name))
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(Params), C.POINTER(Shard), C.POINTER(C.c_float), C.c_int,
+                   C.POINTER(C.c_ulonglong)]
+    if shard is None:
+        shard = Shard(1, 1, 0)
+    rows = len(shard_rows(shard.stripe_rows, shard.n_parts, shard.part, params.height))
+    out = np.empty((rows, params.width, 4), dtype=np.float32)
+    counts = (C.c_ulonglong * 7)()
+    rc = fn(C.byref(params), C.byref(shard), out.ctypes.data_as(C.POINTER(C.c_float)),
+            int(nthreads), counts)
+    if rc != 0:
+        raise RuntimeError("%s_render_%s failed: %d" % (prefix, name, rc))
+    if want_counts:
+        keys = ("sin", "cos", "exp", "pow", "sqrt", "other")
+        return out, dict(zip(keys, [int(c) for c in counts[:6]]))
+    return out
+
+
+def ref_render(app, params, shard=None, nthreads=0, want_counts=False):
+    """The reference's own arithmetic (verbatim headers + shim + glibc libm)."""
+    return _render(_load(REF_SO), "sbxref", app, params, shard, nthreads, want_counts)
+
+
+def oracle_render(app, params, shard=None, nthreads=0, want_counts=False):
+    """The plain-C restatement."""
+    return _render(_load(ORACLE_SO), "sbxoracle", app, params, shard, nthreads, want_counts)
