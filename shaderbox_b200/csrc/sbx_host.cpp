@@ -1,0 +1,596 @@
+// sbx_host.cpp -- the C ABI of include/sbx.h: a host for shaderbox app shaders on one B200.
+//
+// Plain C++ over the CUDA driver API (loaded lazily with dlopen so the library itself loads, and
+// its symbols can be checked, on a machine without a driver).  Kernels come as sm_100a cubins:
+//   images/<APP>.plugin.cubin   an UNCHANGED shaderbox app header compiled by sbx_compile_app
+//   images/<APP>.native.cubin   hand-written scene kernels (when present)
+//   images/sbx_util.cubin       hash-table / unshard / operator-evaluation kernels
+// There is deliberately no CPU path: without a device every render entry fails with an error.
+#include <cuda.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../include/sbx/sbx_launch.h"
+#include "../include/sbx/sbx_math.h"
+#include "sbx_internal.h"
+
+namespace {
+
+// ---- lazily bound driver API ------------------------------------------------------------------
+struct driver_api {
+    void* lib = nullptr;
+    CUresult (*Init)(unsigned);
+    CUresult (*DeviceGet)(CUdevice*, int);
+    CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice);
+    CUresult (*DevicePrimaryCtxRetain)(CUcontext*, CUdevice);
+    CUresult (*DevicePrimaryCtxRelease)(CUdevice);
+    CUresult (*CtxPushCurrent)(CUcontext);
+    CUresult (*CtxPopCurrent)(CUcontext*);
+    CUresult (*ModuleLoadData)(CUmodule*, const void*);
+    CUresult (*ModuleUnload)(CUmodule);
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction);
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t);
+    CUresult (*MemAlloc)(CUdeviceptr*, size_t);
+    CUresult (*MemFree)(CUdeviceptr);
+    CUresult (*MemcpyHtoD)(CUdeviceptr, const void*, size_t);
+    CUresult (*MemcpyDtoH)(void*, CUdeviceptr, size_t);
+    CUresult (*MemcpyDtoHAsync)(void*, CUdeviceptr, size_t, CUstream);
+    CUresult (*MemcpyHtoDAsync)(CUdeviceptr, const void*, size_t, CUstream);
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             CUstream, void**, void**);
+    CUresult (*StreamSynchronize)(CUstream);
+    CUresult (*EventCreate)(CUevent*, unsigned);
+    CUresult (*EventRecord)(CUevent, CUstream);
+    CUresult (*EventSynchronize)(CUevent);
+    CUresult (*EventElapsedTime)(float*, CUevent, CUevent);
+    CUresult (*EventDestroy)(CUevent);
+    CUresult (*GetErrorString)(CUresult, const char**);
+};
+
+std::mutex g_mutex;
+std::string g_last_error;   // for calls without a context
+
+driver_api* load_driver(std::string* err) {
+    static driver_api api;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (api.lib) return &api;
+    void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+        *err = "no CUDA driver (libcuda.so.1 not found): shaderbox_b200 has no CPU path";
+        return nullptr;
+    }
+#define SBX_SYM(field, name)                                                            \
+    *(void**)(&api.field) = dlsym(lib, name);                                           \
+    if (!api.field) { *err = std::string("libcuda lacks ") + name; return nullptr; }
+    SBX_SYM(Init, "cuInit")
+    SBX_SYM(DeviceGet, "cuDeviceGet")
+    SBX_SYM(DeviceGetAttribute, "cuDeviceGetAttribute")
+    SBX_SYM(DevicePrimaryCtxRetain, "cuDevicePrimaryCtxRetain")
+    SBX_SYM(DevicePrimaryCtxRelease, "cuDevicePrimaryCtxRelease_v2")
+    SBX_SYM(CtxPushCurrent, "cuCtxPushCurrent_v2")
+    SBX_SYM(CtxPopCurrent, "cuCtxPopCurrent_v2")
+    SBX_SYM(ModuleLoadData, "cuModuleLoadData")
+    SBX_SYM(ModuleUnload, "cuModuleUnload")
+    SBX_SYM(ModuleGetFunction, "cuModuleGetFunction")
+    SBX_SYM(FuncGetAttribute, "cuFuncGetAttribute")
+    SBX_SYM(FuncSetAttribute, "cuFuncSetAttribute")
+    SBX_SYM(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
+    SBX_SYM(MemAlloc, "cuMemAlloc_v2")
+    SBX_SYM(MemFree, "cuMemFree_v2")
+    SBX_SYM(MemcpyHtoD, "cuMemcpyHtoD_v2")
+    SBX_SYM(MemcpyDtoH, "cuMemcpyDtoH_v2")
+    SBX_SYM(MemcpyDtoHAsync, "cuMemcpyDtoHAsync_v2")
+    SBX_SYM(MemcpyHtoDAsync, "cuMemcpyHtoDAsync_v2")
+    SBX_SYM(LaunchKernel, "cuLaunchKernel")
+    SBX_SYM(StreamSynchronize, "cuStreamSynchronize")
+    SBX_SYM(EventCreate, "cuEventCreate")
+    SBX_SYM(EventRecord, "cuEventRecord")
+    SBX_SYM(EventSynchronize, "cuEventSynchronize")
+    SBX_SYM(EventElapsedTime, "cuEventElapsedTime")
+    SBX_SYM(EventDestroy, "cuEventDestroy_v2")
+    SBX_SYM(GetErrorString, "cuGetErrorString")
+#undef SBX_SYM
+    api.lib = lib;
+    return &api;
+}
+
+struct kernel_image {
+    CUmodule module = nullptr;
+    CUfunction render = nullptr;
+    int regs = 0, max_threads = 0, blocks_per_sm = 0;
+    int warps_per_cta = 4;
+    std::string variant;
+};
+
+bool read_file(const std::string& path, std::string* out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::ostringstream ss;
+    ss << f.rdbuf();
+    *out = ss.str();
+    return true;
+}
+
+}  // namespace
+
+struct sbx_ctx {
+    driver_api* cu = nullptr;
+    int device = 0;
+    CUdevice dev = 0;
+    CUcontext ctx = nullptr;
+    int sm_count = 0;
+    std::string last_error;
+    sbx_timing timing{};
+
+    std::map<std::string, kernel_image> images;   // "APP_X/variant"
+    kernel_image* current = nullptr;
+    std::string current_app;
+
+    CUmodule util_module = nullptr;
+    CUfunction k_hash = nullptr, k_unshard = nullptr, k_eval = nullptr;
+
+    CUdeviceptr lut = 0;          // SBX_LUT_MATH_BYTES
+    CUdeviceptr hash_tab = 0;     // floats
+    int hash_lo = 0, hash_len = 0;
+    int opt_hash_log2 = 18;       // table covers [-2^(k-1), 2^(k-1))
+    int opt_use_hash = 1;
+
+    CUdeviceptr frame = 0;        // internal frame for sbx_render_host
+    size_t frame_bytes = 0;
+    CUevent ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+
+    int fail(int status, const char* fmt, ...) {
+        char buf[2048];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        last_error = buf;
+        return status;
+    }
+    int check(CUresult r, const char* what) {
+        if (r == CUDA_SUCCESS) return SBX_OK;
+        const char* s = nullptr;
+        cu->GetErrorString(r, &s);
+        return fail(SBX_ERR_CUDA, "%s: %s (%d)", what, s ? s : "?", (int)r);
+    }
+};
+
+namespace {
+
+struct ctx_scope {   // make the primary context current for the duration of a call
+    sbx_ctx* c;
+    explicit ctx_scope(sbx_ctx* c_) : c(c_) { c->cu->CtxPushCurrent(c->ctx); }
+    ~ctx_scope() { CUcontext old; c->cu->CtxPopCurrent(&old); }
+};
+
+#define SBX_TRY(expr, what)                                     \
+    do {                                                        \
+        int st_ = ctx->check((expr), what);                     \
+        if (st_ != SBX_OK) return st_;                          \
+    } while (0)
+
+int load_util(sbx_ctx* ctx) {
+    if (ctx->util_module) return SBX_OK;
+    std::string bin;
+    const std::string path = sbx::library_dir() + "/images/sbx_util.cubin";
+    if (!read_file(path, &bin)) return ctx->fail(SBX_ERR_UNKNOWN_APP, "kernel image %s not found (run __graft_entry__.build())", path.c_str());
+    SBX_TRY(ctx->cu->ModuleLoadData(&ctx->util_module, bin.data()), "cuModuleLoadData(sbx_util)");
+    SBX_TRY(ctx->cu->ModuleGetFunction(&ctx->k_hash, ctx->util_module, "sbx_hash_table_kernel"), "get sbx_hash_table_kernel");
+    SBX_TRY(ctx->cu->ModuleGetFunction(&ctx->k_unshard, ctx->util_module, "sbx_unshard_kernel"), "get sbx_unshard_kernel");
+    SBX_TRY(ctx->cu->ModuleGetFunction(&ctx->k_eval, ctx->util_module, "sbx_eval_op_kernel"), "get sbx_eval_op_kernel");
+    return SBX_OK;
+}
+
+// LUT block + lattice-hash memo; (re)built when the table option changes
+int ensure_tables(sbx_ctx* ctx, CUstream stream) {
+    int st = load_util(ctx);
+    if (st != SBX_OK) return st;
+    if (!ctx->lut) {
+        static const sbx_u64 exp2_tab[32] = {SBX_EXP2_TABLE_INIT};
+        static const double log2_tab[32] = {SBX_LOG2_TABLE_INIT};
+        unsigned char block[SBX_LUT_MATH_BYTES];
+        std::memcpy(block, exp2_tab, sizeof exp2_tab);
+        std::memcpy(block + sizeof exp2_tab, log2_tab, sizeof log2_tab);
+        SBX_TRY(ctx->cu->MemAlloc(&ctx->lut, SBX_LUT_MATH_BYTES), "cuMemAlloc(lut)");
+        SBX_TRY(ctx->cu->MemcpyHtoD(ctx->lut, block, SBX_LUT_MATH_BYTES), "cuMemcpyHtoD(lut)");
+    }
+    const int want_len = ctx->opt_use_hash ? (1 << ctx->opt_hash_log2) : 0;
+    if (want_len != ctx->hash_len) {
+        if (ctx->hash_tab) { ctx->cu->StreamSynchronize(stream); ctx->cu->MemFree(ctx->hash_tab); ctx->hash_tab = 0; }
+        ctx->hash_len = 0;
+        if (want_len > 0) {
+            SBX_TRY(ctx->cu->MemAlloc(&ctx->hash_tab, (size_t)want_len * sizeof(float)), "cuMemAlloc(hash table)");
+            int lo = -(want_len / 2), len = want_len;
+            void* args[] = {&ctx->hash_tab, &lo, &len, &ctx->lut};
+            SBX_TRY(ctx->cu->LaunchKernel(ctx->k_hash, (unsigned)((len + 255) / 256), 1, 1, 256, 1, 1,
+                                          SBX_LUT_MATH_BYTES, stream, args, nullptr),
+                    "launch sbx_hash_table_kernel");
+            ctx->hash_lo = lo;
+            ctx->hash_len = len;
+            ctx->timing.launches += 1;
+        }
+    }
+    return SBX_OK;
+}
+
+int bind_image(sbx_ctx* ctx, const std::string& key, const std::string& cubin, const std::string& variant) {
+    kernel_image img;
+    SBX_TRY(ctx->cu->ModuleLoadData(&img.module, cubin.data()), "cuModuleLoadData(app image)");
+    SBX_TRY(ctx->cu->ModuleGetFunction(&img.render, img.module, "sbx_render"), "cuModuleGetFunction(sbx_render)");
+    ctx->cu->FuncGetAttribute(&img.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, img.render);
+    ctx->cu->FuncGetAttribute(&img.max_threads, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, img.render);
+    img.warps_per_cta = img.max_threads >= 32 ? img.max_threads / 32 : 4;   // __launch_bounds__ = CTA size
+    ctx->cu->OccupancyMaxActiveBlocksPerMultiprocessor(&img.blocks_per_sm, img.render, img.warps_per_cta * 32,
+                                                       SBX_LUT_MATH_BYTES);
+    img.variant = variant;
+    auto it = ctx->images.find(key);
+    if (it != ctx->images.end() && it->second.module) ctx->cu->ModuleUnload(it->second.module);
+    ctx->images[key] = img;
+    return SBX_OK;
+}
+
+bool valid_shard(const sbx_shard* s, sbx_shard* out) {
+    sbx_shard r = {1, 1, 0};
+    if (s && s->n_parts > 0) r = *s;
+    if (r.stripe_rows <= 0) r.stripe_rows = 1;
+    if (r.part < 0 || r.part >= r.n_parts) return false;
+    *out = r;
+    return true;
+}
+
+int shard_rows(const sbx_shard& s, int height) {
+    int rows = 0;
+    const int period = s.stripe_rows * s.n_parts;
+    const int full = height / period;
+    rows = full * s.stripe_rows;
+    const int rem = height - full * period;            // rows of the last, partial period
+    const int start = s.part * s.stripe_rows;
+    if (rem > start) rows += (rem - start < s.stripe_rows) ? rem - start : s.stripe_rows;
+    return rows;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sbx_version(void) { return "shaderbox_b200 0.1 (sm_100a)"; }
+
+const char* sbx_strerror(int status) {
+    switch (status) {
+        case SBX_OK: return "ok";
+        case SBX_ERR_INVALID: return "invalid argument";
+        case SBX_ERR_NO_DEVICE: return "no usable CUDA device";
+        case SBX_ERR_UNKNOWN_APP: return "unknown app / kernel image missing";
+        case SBX_ERR_CUDA: return "CUDA call failed";
+        case SBX_ERR_COMPILE: return "app header failed to compile";
+        case SBX_ERR_NOMEM: return "out of memory";
+        case SBX_ERR_UNSUPPORTED: return "unsupported";
+        default: return "unknown status";
+    }
+}
+
+const char* sbx_last_error(sbx_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+
+int sbx_default_params(sbx_params* p, int width, int height) {
+    if (!p || width <= 0 || height <= 0) return SBX_ERR_INVALID;
+    std::memset(p, 0, sizeof *p);
+    p->width = width;
+    p->height = height;
+    p->u_time = 0.0f;
+    // src/uniform_buffer.h:41-54
+    p->wind_dir[0] = 0.0f; p->wind_dir[1] = 0.0f; p->wind_dir[2] = 0.2f;
+    p->sun_dir[0] = 0.0f; p->sun_dir[1] = 0.0f; p->sun_dir[2] = -1.0f;
+    p->sun_color[0] = 1.0f; p->sun_color[1] = 0.7f; p->sun_color[2] = 0.55f;
+    p->sun_power = 8.0f;
+    p->cld_march_steps = 100;
+    p->illum_march_steps = 6;
+    p->sigma_scattering = 0.15f;
+    p->cld_coverage = 0.535f;
+    p->cld_thick = 125.0f;
+    p->atm_radius = 5000.0f;
+    p->atm_ground_y = 4750.0f;
+    // src/uniform_buffer.h:57-58
+    p->fog_density = 0.1f;
+    p->fog_falloff = 0.5f;
+    return SBX_OK;
+}
+
+int sbx_create(int device, sbx_ctx** out) {
+    if (!out) return SBX_ERR_INVALID;
+    *out = nullptr;
+    std::string err;
+    driver_api* cu = load_driver(&err);
+    if (!cu) { g_last_error = err; return SBX_ERR_NO_DEVICE; }
+    if (cu->Init(0) != CUDA_SUCCESS) { g_last_error = "cuInit failed: no usable CUDA device"; return SBX_ERR_NO_DEVICE; }
+    sbx_ctx* ctx = new sbx_ctx;
+    ctx->cu = cu;
+    ctx->device = device;
+    if (cu->DeviceGet(&ctx->dev, device) != CUDA_SUCCESS) {
+        g_last_error = "cuDeviceGet failed";
+        delete ctx;
+        return SBX_ERR_NO_DEVICE;
+    }
+    int major = 0, minor = 0;
+    cu->DeviceGetAttribute(&major, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, ctx->dev);
+    cu->DeviceGetAttribute(&minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, ctx->dev);
+    cu->DeviceGetAttribute(&ctx->sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, ctx->dev);
+    if (major != 10) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "device %d is sm_%d%d; the kernel images are sm_100a only", device, major, minor);
+        g_last_error = buf;
+        delete ctx;
+        return SBX_ERR_NO_DEVICE;
+    }
+    if (cu->DevicePrimaryCtxRetain(&ctx->ctx, ctx->dev) != CUDA_SUCCESS) {
+        g_last_error = "cuDevicePrimaryCtxRetain failed";
+        delete ctx;
+        return SBX_ERR_CUDA;
+    }
+    {
+        ctx_scope scope(ctx);
+        cu->EventCreate(&ctx->ev0, CU_EVENT_DEFAULT);
+        cu->EventCreate(&ctx->ev1, CU_EVENT_DEFAULT);
+        cu->EventCreate(&ctx->ev2, CU_EVENT_DEFAULT);
+    }
+    *out = ctx;
+    return SBX_OK;
+}
+
+void sbx_destroy(sbx_ctx* ctx) {
+    if (!ctx) return;
+    {
+        ctx_scope scope(ctx);
+        for (auto& kv : ctx->images)
+            if (kv.second.module) ctx->cu->ModuleUnload(kv.second.module);
+        if (ctx->util_module) ctx->cu->ModuleUnload(ctx->util_module);
+        if (ctx->lut) ctx->cu->MemFree(ctx->lut);
+        if (ctx->hash_tab) ctx->cu->MemFree(ctx->hash_tab);
+        if (ctx->frame) ctx->cu->MemFree(ctx->frame);
+        if (ctx->ev0) ctx->cu->EventDestroy(ctx->ev0);
+        if (ctx->ev1) ctx->cu->EventDestroy(ctx->ev1);
+        if (ctx->ev2) ctx->cu->EventDestroy(ctx->ev2);
+    }
+    ctx->cu->DevicePrimaryCtxRelease(ctx->dev);
+    delete ctx;
+}
+
+int sbx_compile_app(sbx_ctx* ctx, const char* app_header_path, const char* app_name, const char* image_out_path) {
+    if (!app_header_path || !app_name) return SBX_ERR_INVALID;
+    std::string cubin, log;
+    const int st = sbx::compile_app_header(app_header_path, app_name, {}, &cubin, &log);
+    if (st != SBX_OK) {
+        if (ctx) ctx->last_error = log; else g_last_error = log;
+        return st;
+    }
+    if (image_out_path) {
+        std::ofstream f(image_out_path, std::ios::binary);
+        if (!f) { g_last_error = std::string("cannot write ") + image_out_path; return SBX_ERR_INVALID; }
+        f.write(cubin.data(), (std::streamsize)cubin.size());
+    }
+    if (ctx) {
+        ctx_scope scope(ctx);
+        const std::string key = std::string(app_name) + "/plugin";
+        const int bs = bind_image(ctx, key, cubin, "plugin");
+        if (bs != SBX_OK) return bs;
+        ctx->last_error = log;   // warnings, if any
+    } else {
+        g_last_error = log;
+    }
+    return SBX_OK;
+}
+
+int sbx_load_app(sbx_ctx* ctx, const char* app_name, const char* variant) {
+    if (!ctx || !app_name) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    const char* order_default[] = {"native", "plugin"};
+    std::vector<std::string> order;
+    if (variant && *variant) order.push_back(variant);
+    else for (const char* v : order_default) order.push_back(v);
+    for (const auto& v : order) {
+        const std::string key = std::string(app_name) + "/" + v;
+        auto it = ctx->images.find(key);
+        if (it == ctx->images.end()) {
+            std::string bin;
+            const std::string path = sbx::library_dir() + "/images/" + app_name + "." + v + ".cubin";
+            if (!read_file(path, &bin)) continue;
+            const int st = bind_image(ctx, key, bin, v);
+            if (st != SBX_OK) return st;
+            it = ctx->images.find(key);
+        }
+        ctx->current = &it->second;
+        ctx->current_app = app_name;
+        return SBX_OK;
+    }
+    return ctx->fail(SBX_ERR_UNKNOWN_APP, "no kernel image for %s (variant %s) under %s/images", app_name,
+                     variant && *variant ? variant : "native|plugin", sbx::library_dir().c_str());
+}
+
+int sbx_shard_rows(const sbx_shard* shard, int height) {
+    sbx_shard s;
+    if (height <= 0 || !valid_shard(shard, &s)) return SBX_ERR_INVALID;
+    return shard_rows(s, height);
+}
+
+int sbx_set_option(sbx_ctx* ctx, const char* key, int value) {
+    if (!ctx || !key) return SBX_ERR_INVALID;
+    if (!std::strcmp(key, "hash_table_log2")) {
+        if (value < 9 || value > 22) return SBX_ERR_INVALID;
+        ctx->opt_hash_log2 = value;
+        return SBX_OK;
+    }
+    if (!std::strcmp(key, "use_hash_table")) { ctx->opt_use_hash = value ? 1 : 0; return SBX_OK; }
+    return SBX_ERR_INVALID;
+}
+
+int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_rgba, void* stream_) {
+    if (!ctx || !p || !dev_rgba || p->width <= 0 || p->height <= 0) return SBX_ERR_INVALID;
+    if (!ctx->current) return ctx->fail(SBX_ERR_UNKNOWN_APP, "sbx_load_app was not called");
+    sbx_shard s;
+    if (!valid_shard(shard, &s)) return ctx->fail(SBX_ERR_INVALID, "bad shard");
+    CUstream stream = (CUstream)stream_;
+    ctx_scope scope(ctx);
+    ctx->timing.launches = 0;
+    int st = ensure_tables(ctx, stream);
+    if (st != SBX_OK) return st;
+
+    sbx_launch L;
+    std::memset(&L, 0, sizeof L);
+    L.p = *p;
+    L.stripe_rows = s.stripe_rows;
+    L.n_parts = s.n_parts;
+    L.part = s.part;
+    L.local_rows = shard_rows(s, p->height);
+    if (L.local_rows == 0) return SBX_OK;
+    L.tiles_x = (p->width + SBX_TILE_W - 1) / SBX_TILE_W;
+    L.tiles_y = (L.local_rows + SBX_TILE_H - 1) / SBX_TILE_H;
+    L.out = dev_rgba;
+    L.hash_tab = (const float*)ctx->hash_tab;
+    L.hash_bias = SBX_HASH_MAGIC_BITS + ctx->hash_lo;
+    L.hash_len = ctx->hash_len;
+    L.hash_span = ctx->hash_len > 271 ? ctx->hash_len - 271 : 0;
+    L.lut = (const void*)ctx->lut;
+
+    kernel_image* img = ctx->current;
+    const long long tiles = (long long)L.tiles_x * L.tiles_y;
+    const unsigned grid = (unsigned)((tiles + img->warps_per_cta - 1) / img->warps_per_cta);
+    void* args[] = {&L};
+    SBX_TRY(ctx->cu->EventRecord(ctx->ev0, stream), "cuEventRecord");
+    SBX_TRY(ctx->cu->LaunchKernel(img->render, grid, 1, 1, (unsigned)img->warps_per_cta * 32, 1, 1,
+                                  SBX_LUT_MATH_BYTES, stream, args, nullptr),
+            "launch sbx_render");
+    SBX_TRY(ctx->cu->EventRecord(ctx->ev1, stream), "cuEventRecord");
+    ctx->timing.launches += 1;
+    ctx->timing.grid_blocks = (int)grid;
+    ctx->timing.block_threads = img->warps_per_cta * 32;
+    ctx->timing.regs_per_thread = img->regs;
+    ctx->timing.blocks_per_sm = img->blocks_per_sm;
+    ctx->timing.kernel_ms = -1.0f;   // resolved lazily by sbx_last_timing
+    ctx->timing.d2h_ms = 0.0f;
+    return SBX_OK;
+}
+
+int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* host_rgba) {
+    if (!ctx || !p || !host_rgba || p->width <= 0 || p->height <= 0) return SBX_ERR_INVALID;
+    sbx_shard s;
+    if (!valid_shard(shard, &s)) return ctx->fail(SBX_ERR_INVALID, "bad shard");
+    const size_t bytes = (size_t)shard_rows(s, p->height) * (size_t)p->width * 4 * sizeof(float);
+    if (bytes == 0) return SBX_OK;
+    {
+        ctx_scope scope(ctx);
+        if (bytes > ctx->frame_bytes) {
+            if (ctx->frame) ctx->cu->MemFree(ctx->frame);
+            ctx->frame = 0;
+            ctx->frame_bytes = 0;
+            if (ctx->cu->MemAlloc(&ctx->frame, bytes) != CUDA_SUCCESS) return ctx->fail(SBX_ERR_NOMEM, "cuMemAlloc(%zu) failed", bytes);
+            ctx->frame_bytes = bytes;
+        }
+    }
+    int st = sbx_render_device(ctx, p, &s, (float*)ctx->frame, nullptr);
+    if (st != SBX_OK) return st;
+    ctx_scope scope(ctx);
+    SBX_TRY(ctx->cu->MemcpyDtoHAsync(host_rgba, ctx->frame, bytes, nullptr), "cuMemcpyDtoHAsync");
+    SBX_TRY(ctx->cu->EventRecord(ctx->ev2, nullptr), "cuEventRecord");
+    SBX_TRY(ctx->cu->StreamSynchronize(nullptr), "cuStreamSynchronize");
+    float ms = 0.0f;
+    if (ctx->cu->EventElapsedTime(&ms, ctx->ev1, ctx->ev2) == CUDA_SUCCESS) ctx->timing.d2h_ms = ms;
+    return SBX_OK;
+}
+
+int sbx_unshard_device(sbx_ctx* ctx, int width, int height, const sbx_shard* shard, const float* dev_part,
+                       float* dev_frame, void* stream_) {
+    if (!ctx || !dev_part || !dev_frame || width <= 0 || height <= 0) return SBX_ERR_INVALID;
+    sbx_shard s;
+    if (!valid_shard(shard, &s)) return ctx->fail(SBX_ERR_INVALID, "bad shard");
+    ctx_scope scope(ctx);
+    int st = load_util(ctx);
+    if (st != SBX_OK) return st;
+    int rows = shard_rows(s, height);
+    if (rows == 0) return SBX_OK;
+    const long long total = (long long)rows * width;
+    void* args[] = {(void*)&dev_part, (void*)&dev_frame, &width, &rows, &s.stripe_rows, &s.n_parts, &s.part};
+    SBX_TRY(ctx->cu->LaunchKernel(ctx->k_unshard, (unsigned)((total + 255) / 256), 1, 1, 256, 1, 1, 0,
+                                  (CUstream)stream_, args, nullptr),
+            "launch sbx_unshard_kernel");
+    return SBX_OK;
+}
+
+int sbx_last_timing(sbx_ctx* ctx, sbx_timing* out) {
+    if (!ctx || !out) return SBX_ERR_INVALID;
+    if (ctx->timing.kernel_ms < 0.0f && ctx->ev1) {
+        ctx_scope scope(ctx);
+        float ms = 0.0f;
+        if (ctx->cu->EventSynchronize(ctx->ev1) == CUDA_SUCCESS &&
+            ctx->cu->EventElapsedTime(&ms, ctx->ev0, ctx->ev1) == CUDA_SUCCESS)
+            ctx->timing.kernel_ms = ms;
+    }
+    *out = ctx->timing;
+    return SBX_OK;
+}
+
+static int op_code(const char* op) {
+    static const struct { const char* name; int code; } table[] = {
+        {"sinf", 0}, {"cosf", 1}, {"tanf", 2}, {"expf", 3}, {"powf", 4}, {"acosf", 5}, {"atan2f", 6}, {"sqrtf", 7}, {"divf", 8},
+        {"hash", 16}, {"hash_arith", 17}, {"noise_iq", 18}, {"noise_w", 19}, {"fbm4", 20}, {"fbm_w3", 21},
+        {"sd_sphere", 32}, {"sd_box", 33}, {"sd_torus", 34}, {"sd_y_cylinder", 35}, {"sd_cylinder", 36}, {"sd_bezier", 37},
+        {"sd_capsule", 38}, {"sd_plane", 39}, {"op_blend", 40}, {"ik_solver", 41},
+        {"henyey_greenstein_phase_func", 48}, {"rayleigh_phase_func", 49}, {"schlick_phase_func", 50},
+        {"isotropic_phase_func", 51}, {"fresnel_factor", 52}, {"reflect", 53}, {"refract", 54},
+        {"illum_cook_torrance", 55}, {"illum_blinn_phong", 56}, {"intersect_sphere", 57}, {"intersect_plane", 58},
+        {"rotate_around_x", 64}, {"rotate_around_y", 65}, {"rotate_around_z", 66}, {"linear_to_srgb", 67}, {"band", 68},
+        {"checkboard_pattern", 69}, {"remap", 70}, {"get_primary_ray", 71}, {"smoothstep", 72}, {"mod", 73},
+        {"fast_orthonormal_basis", 74}};
+    for (const auto& e : table)
+        if (!std::strcmp(e.name, op)) return e.code;
+    return -1;
+}
+
+int sbx_eval_op(sbx_ctx* ctx, const char* op, const float* in, int in_stride, float* out, int out_stride, int n) {
+    if (!ctx || !op || !in || !out || in_stride <= 0 || out_stride <= 0 || n < 0) return SBX_ERR_INVALID;
+    int code = op_code(op);
+    if (code < 0) return ctx->fail(SBX_ERR_UNSUPPORTED, "unknown operator %s", op);
+    if (n == 0) return SBX_OK;
+    ctx_scope scope(ctx);
+    int st = ensure_tables(ctx, nullptr);
+    if (st != SBX_OK) return st;
+    CUdeviceptr din = 0, dout = 0;
+    const size_t in_bytes = (size_t)n * in_stride * sizeof(float), out_bytes = (size_t)n * out_stride * sizeof(float);
+    SBX_TRY(ctx->cu->MemAlloc(&din, in_bytes), "cuMemAlloc");
+    if (ctx->cu->MemAlloc(&dout, out_bytes) != CUDA_SUCCESS) { ctx->cu->MemFree(din); return ctx->fail(SBX_ERR_NOMEM, "cuMemAlloc"); }
+    sbx_launch L;
+    std::memset(&L, 0, sizeof L);
+    sbx_default_params(&L.p, 1, 1);
+    L.hash_tab = (const float*)ctx->hash_tab;
+    L.hash_bias = SBX_HASH_MAGIC_BITS + ctx->hash_lo;
+    L.hash_len = ctx->hash_len;
+    L.hash_span = ctx->hash_len > 271 ? ctx->hash_len - 271 : 0;
+    L.lut = (const void*)ctx->lut;
+    int rc = SBX_OK;
+    do {
+        if ((rc = ctx->check(ctx->cu->MemcpyHtoD(din, in, in_bytes), "cuMemcpyHtoD")) != SBX_OK) break;
+        if ((rc = ctx->check(ctx->cu->MemcpyHtoD(dout, out, out_bytes), "cuMemcpyHtoD")) != SBX_OK) break;
+        void* args[] = {&L, &code, &din, &in_stride, &dout, &out_stride, &n};
+        if ((rc = ctx->check(ctx->cu->LaunchKernel(ctx->k_eval, (unsigned)((n + 127) / 128), 1, 1, 128, 1, 1,
+                                                   SBX_LUT_MATH_BYTES, nullptr, args, nullptr),
+                             "launch sbx_eval_op_kernel")) != SBX_OK) break;
+        if ((rc = ctx->check(ctx->cu->MemcpyDtoH(out, dout, out_bytes), "cuMemcpyDtoH")) != SBX_OK) break;
+    } while (0);
+    ctx->cu->MemFree(din);
+    ctx->cu->MemFree(dout);
+    return rc;
+}
+
+}  // extern "C"

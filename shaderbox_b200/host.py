@@ -1,0 +1,156 @@
+"""Host-side mirror of the reference's plugin interface over the C ABI (include/sbx.h).
+
+A shaderbox "host" provides u_res / u_time / u_mouse (+ the aux uniform block) and calls
+mainImage once per pixel (src/main.h:6-53, src/uniform_buffer.h:26-58).  `Renderer` is that host:
+it selects an app by its reference define (src/Makefile:9, `-DAPP_PLANET`), takes the uniforms as
+keyword arguments under their reference names, and returns the RGBA32F frame.
+
+This module is plumbing only: ctypes calls into shaderbox_b200/libsbx.so.  There is no Python or
+CPU implementation of the pixel path here -- if the library or a B200 is missing, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .abi import Params, Shard, Timing, default_params, shard_rows, SBX_OK
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsbx.so")
+
+_lib = None
+
+
+class SbxError(RuntimeError):
+    def __init__(self, status, where, detail=""):
+        self.status = status
+        super().__init__("%s failed: %d %s" % (where, status, detail))
+
+
+def lib():
+    """Load libsbx.so (built in-tree by __graft_entry__.build()); raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SbxError(-2, "load", "%s not built (run `python -c 'import __graft_entry__ as g; g.build()'`)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        P = C.POINTER
+        L.sbx_version.restype = C.c_char_p
+        L.sbx_strerror.restype = C.c_char_p
+        L.sbx_strerror.argtypes = [C.c_int]
+        L.sbx_last_error.restype = C.c_char_p
+        L.sbx_last_error.argtypes = [C.c_void_p]
+        L.sbx_default_params.argtypes = [P(Params), C.c_int, C.c_int]
+        L.sbx_create.argtypes = [C.c_int, P(C.c_void_p)]
+        L.sbx_destroy.argtypes = [C.c_void_p]
+        L.sbx_destroy.restype = None
+        L.sbx_load_app.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.sbx_compile_app.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.sbx_shard_rows.argtypes = [P(Shard), C.c_int]
+        L.sbx_render_device.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_void_p]
+        L.sbx_render_host.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p]
+        L.sbx_unshard_device.argtypes = [C.c_void_p, C.c_int, C.c_int, P(Shard), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sbx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.sbx_last_timing.argtypes = [C.c_void_p, P(Timing)]
+        L.sbx_eval_op.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        _lib = L
+    return _lib
+
+
+EXPORTS = (
+    "sbx_default_params", "sbx_create", "sbx_destroy", "sbx_load_app", "sbx_compile_app", "sbx_shard_rows",
+    "sbx_render_device", "sbx_render_host", "sbx_unshard_device", "sbx_set_option", "sbx_last_timing",
+    "sbx_last_error", "sbx_strerror", "sbx_version", "sbx_eval_op",
+)
+
+
+def compile_app(header_path, app_name, image_out_path):
+    """Compile an unchanged shaderbox app header to an sm_100a kernel image (no GPU needed)."""
+    L = lib()
+    rc = L.sbx_compile_app(None, os.fsencode(header_path), app_name.encode(), os.fsencode(image_out_path))
+    if rc != SBX_OK:
+        raise SbxError(rc, "sbx_compile_app", (L.sbx_last_error(None) or b"").decode(errors="replace"))
+    return image_out_path
+
+
+class Renderer:
+    """One context on one GPU.  Usage:  r = Renderer("APP_CLOUDS"); img = r.render(1920, 1080, u_time=1.5)"""
+
+    def __init__(self, app, device=0, variant=None):
+        self._L = lib()
+        self._ctx = C.c_void_p()
+        rc = self._L.sbx_create(int(device), C.byref(self._ctx))
+        if rc != SBX_OK:
+            raise SbxError(rc, "sbx_create", (self._L.sbx_last_error(None) or b"").decode(errors="replace"))
+        self.app = None
+        self.load_app(app, variant)
+
+    def _check(self, rc, where):
+        if rc != SBX_OK:
+            raise SbxError(rc, where, (self._L.sbx_last_error(self._ctx) or b"").decode(errors="replace"))
+
+    def load_app(self, app, variant=None):
+        self._check(self._L.sbx_load_app(self._ctx, app.encode(), variant.encode() if variant else None), "sbx_load_app")
+        self.app = app
+
+    def set_option(self, key, value):
+        self._check(self._L.sbx_set_option(self._ctx, key.encode(), int(value)), "sbx_set_option")
+
+    def close(self):
+        if self._ctx:
+            self._L.sbx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def params(width, height, u_time=0.0, **uniforms):
+        return default_params(width, height, u_time, **uniforms)
+
+    def render(self, width, height, u_time=0.0, shard=None, out=None, **uniforms):
+        """Render to host memory; returns float32 [rows, width, 4] (row 0 = fragCoord.y 0.5)."""
+        p = uniforms.pop("params", None) or default_params(width, height, u_time, **uniforms)
+        sh = Shard(*shard) if shard is not None else Shard(1, 1, 0)
+        rows = len(shard_rows(sh.stripe_rows, sh.n_parts, sh.part, p.height))
+        if out is None:
+            out = np.empty((rows, p.width, 4), dtype=np.float32)
+        assert out.dtype == np.float32 and out.size == rows * p.width * 4 and out.flags["C_CONTIGUOUS"]
+        self._check(self._L.sbx_render_host(self._ctx, C.byref(p), C.byref(sh), out.ctypes.data_as(C.c_void_p)),
+                    "sbx_render_host")
+        return out
+
+    def render_into(self, params, dev_ptr, shard=None, stream=0):
+        """Render into device memory at `dev_ptr` (e.g. a torch tensor's data_ptr()) on `stream`."""
+        sh = Shard(*shard) if shard is not None else Shard(1, 1, 0)
+        self._check(self._L.sbx_render_device(self._ctx, C.byref(params), C.byref(sh), C.c_void_p(dev_ptr),
+                                              C.c_void_p(stream)), "sbx_render_device")
+
+    def render_host_ptr(self, params, host_ptr, shard=None):
+        """Render + copy to a host buffer given by address (e.g. a pinned torch tensor)."""
+        sh = Shard(*shard) if shard is not None else Shard(1, 1, 0)
+        self._check(self._L.sbx_render_host(self._ctx, C.byref(params), C.byref(sh), C.c_void_p(host_ptr)),
+                    "sbx_render_host")
+
+    def unshard(self, width, height, shard, dev_part, dev_frame, stream=0):
+        sh = Shard(*shard)
+        self._check(self._L.sbx_unshard_device(self._ctx, width, height, C.byref(sh), C.c_void_p(dev_part),
+                                               C.c_void_p(dev_frame), C.c_void_p(stream)), "sbx_unshard_device")
+
+    def timing(self):
+        t = Timing()
+        self._check(self._L.sbx_last_timing(self._ctx, C.byref(t)), "sbx_last_timing")
+        return {k: getattr(t, k) for k, _ in Timing._fields_}
+
+    def eval_op(self, op, inputs, out_width):
+        """Evaluate one operator of the device library on the rows of `inputs` (test hook)."""
+        a = np.ascontiguousarray(inputs, dtype=np.float32)
+        if a.ndim == 1:
+            a = a[:, None]
+        out = np.zeros((a.shape[0], out_width), dtype=np.float32)
+        self._check(self._L.sbx_eval_op(self._ctx, op.encode(), a.ctypes.data_as(C.c_void_p), a.shape[1],
+                                        out.ctypes.data_as(C.c_void_p), out_width, a.shape[0]), "sbx_eval_op")
+        return out

@@ -1,0 +1,113 @@
+// sbx_kernel.cuh -- the pixel loop as a CUDA grid (replaces the host loops of the reference:
+// VML's SDL_app.cpp, src/Makefile:21, and hlsltoy's fullscreen triangle,
+// util/hlsltoy/src/hlsltoy.cpp:494-495).
+//
+// Translation unit layout (assembled by sbx_compile_app with NVRTC, -default-device):
+//     -DAPP_xxx -DSBX_APP_HEADER="<the app header, float literals suffixed>"
+//     #include "sbx/sbx_kernel.cuh"
+// The UNCHANGED app header is included inside `struct sbx_app`, so its file-scope state becomes
+// per-pixel members and its free functions become __device__ members; the library headers it
+// pulls in ("def.h", "sdf.h", "noise_iq.h", ...) resolve to this directory.
+//
+// Mapping: one thread per pixel; a warp owns an 8x4 pixel tile (each tile row is one 128-byte
+// line of the RGBA32F frame, so a warp's store is four full lines); a CTA is SBX_WARPS_PER_CTA
+// warps on consecutive tiles.  The prologue stages the math LUT block from HBM to shared memory
+// with one TMA bulk copy (cp.async.bulk) completing on an mbarrier.
+#ifndef SBX_KERNEL_CUH_
+#define SBX_KERNEL_CUH_
+
+#include "sbx_launch.h"
+#include "sbx_vec.cuh"
+
+#ifndef SBX_WARPS_PER_CTA
+#define SBX_WARPS_PER_CTA 4
+#endif
+#ifndef SBX_MIN_CTAS_PER_SM
+#define SBX_MIN_CTAS_PER_SM 1
+#endif
+
+// ---- TMA bulk copy of the LUT block: global -> shared, completion on an mbarrier --------------
+__device__ __forceinline__ unsigned sbx_smem_addr(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void sbx_stage_lut(const void* lut_global) {
+    __shared__ __align__(8) unsigned long long sbx_lut_bar;
+    const unsigned bar = sbx_smem_addr(&sbx_lut_bar);
+    const unsigned dst = sbx_smem_addr(sbx_smem);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(SBX_LUT_MATH_BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(dst), "l"(lut_global), "n"(SBX_LUT_MATH_BYTES), "r"(bar) : "memory");
+    }
+    // every thread waits for phase 0 of the barrier
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar) : "memory");
+    }
+}
+
+namespace sbx_glsl {
+
+// uniform loaders used by uniform_buffer.h's _uniform()
+SBX_FN float sbx_uniform(const float& v) { return v; }
+SBX_FN int sbx_uniform(const int& v) { return v; }
+SBX_FN vec3 sbx_uniform(const float (&v)[3]) { return vec3(v[0], v[1], v[2]); }
+// read before uniform_buffer.h turns u_time / u_mouse into macros
+SBX_FN float sbx_param_time(const sbx_launch* L) { return L->p.u_time; }
+SBX_FN vec4 sbx_param_mouse(const sbx_launch* L) {
+    return vec4(L->p.u_mouse[0], L->p.u_mouse[1], L->p.u_mouse[2], L->p.u_mouse[3]);
+}
+
+struct sbx_app {
+    const sbx_launch* __restrict__ sbx_L;   // must stay the first member (see uniform_buffer.h)
+    // what the host provides to the C++ build of the reference (src/uniform_buffer.h:32-36)
+    vec2 iResolution;
+    float iGlobalTime;
+    vec4 iMouse;
+
+#include SBX_APP_HEADER
+
+    __device__ __forceinline__ explicit sbx_app(const sbx_launch* L)
+        : sbx_L(L),
+          iResolution(float(L->p.width), float(L->p.height)),
+          iGlobalTime(sbx_param_time(L)),
+          iMouse(sbx_param_mouse(L)) {}
+};
+
+}  // namespace sbx_glsl
+
+extern "C" __global__ void __launch_bounds__(SBX_WARPS_PER_CTA * 32, SBX_MIN_CTAS_PER_SM)
+sbx_render(const __grid_constant__ sbx_launch L) {
+    sbx_stage_lut(L.lut);
+
+    const int warp = blockIdx.x * SBX_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int tile_x = warp % L.tiles_x;
+    const int tile_y = warp / L.tiles_x;
+    const int x = tile_x * SBX_TILE_W + (lane & (SBX_TILE_W - 1));
+    const int lr = tile_y * SBX_TILE_H + (lane / SBX_TILE_W);
+    if (x >= L.p.width || lr >= L.local_rows) return;
+
+    // local (compacted) row -> frame row of this shard
+    const int y = ((lr / L.stripe_rows) * L.n_parts + L.part) * L.stripe_rows + lr % L.stripe_rows;
+
+    sbx_glsl::sbx_app app(&L);
+    sbx_glsl::vec4 c;
+    app.mainImage(c, sbx_glsl::vec2(float(x) + 0.5f, float(y) + 0.5f));
+
+    float4* dst = reinterpret_cast<float4*>(L.out) + (size_t)lr * (size_t)L.p.width + (size_t)x;
+    __stcs(dst, make_float4(c.x, c.y, c.z, c.w));
+}
+
+#endif  // SBX_KERNEL_CUH_

@@ -1,0 +1,26 @@
+// sbx_launch.h -- the kernel parameter block shared by the host launcher and every render kernel.
+#ifndef SBX_LAUNCH_H_
+#define SBX_LAUNCH_H_
+#include "sbx.h"
+
+#define SBX_TILE_W 8          /* a warp renders an 8 x 4 pixel tile */
+#define SBX_TILE_H 4
+#define SBX_HASH_MAGIC_BITS 0x4B400000   /* bits of 1.5*2^23: float(n) + 1.5*2^23 has n in its low mantissa */
+
+typedef struct sbx_launch {
+    sbx_params p;               /* uniforms (u_res/u_time/u_mouse + aux block) */
+    /* rows: local row lr of this launch is frame row ((lr / stripe) * parts + part) * stripe + lr % stripe */
+    int stripe_rows, n_parts, part;
+    int local_rows;             /* rows rendered by this launch */
+    int tiles_x, tiles_y;       /* warp tiles covering width x local_rows */
+    float* out;                 /* local_rows * width float4, compacted */
+    /* memoised lattice hash (noise_iq.h): hash_tab[k] = hash(hash_lo + k), 0 <= k < hash_len */
+    const float* hash_tab;
+    int hash_bias;              /* SBX_HASH_MAGIC_BITS + hash_lo */
+    int hash_len;
+    int hash_span;              /* hash_len - 271: largest base index whose 8 corners are all tabulated */
+    int pad0;
+    const void* lut;            /* SBX_LUT_MATH_BYTES of exp2/log2 tables in global memory (sbx_math.h) */
+} sbx_launch;
+
+#endif
