@@ -46,6 +46,8 @@ def _render(lib, prefix, app, params, shard=None, nthreads=0, want_counts=False)
     rows = len(shard_rows(shard.stripe_rows, shard.n_parts, shard.part, params.height))
     out = np.empty((rows, params.width, 4), dtype=np.float32)
     counts = (C.c_ulonglong * 7)()
+    if nthreads <= 0:
+        nthreads = os.cpu_count() or 1
     rc = fn(C.byref(params), C.byref(shard), out.ctypes.data_as(C.POINTER(C.c_float)),
             int(nthreads), counts)
     if rc != 0:
