@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixels/s of the shaderbox per-pixel path (BASELINE.json: APP_CLOUDS at 1920x1080).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one frame: every pixel's mainImage (src/main.h:6-53 -> src/app_clouds.h:204-218) for the
+uniforms (u_res, u_time, aux block).  There is no input data besides those uniforms; the frame is the
+output (RGBA32F, 16 B/pixel).
+
+  value      frames stay in HBM: CUDA events around each step's launches on the launching stream
+  e2e        the reference-facing call (sbx_render_host through the C ABI): uniforms from the host,
+             frame copied back to pinned host memory, wall time around the synchronous calls
+  roofline   mandated HBM figure (16 B/pixel written / kernel time / measured copy peak) -- and the
+             FP32-issue figure that actually bounds this path (DESIGN.md "Roofline")
+  cpu_baseline  oracle/_ref (the reference's own headers compiled for the host, AVX2+FMA fast-math
+             build, all cores) on a bounded sample of rows of the same frame
+
+N > 1: the frame is cut into 4-row stripes dealt round-robin to the ranks (strong scaling); every
+step ends with the frame assembled on rank 0 (see shaderbox_b200/multi.py), inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "clouds1080": ("APP_CLOUDS", 1920, 1080, 1.5, {"cld_march_steps": 128}),
+    "clouds1080_default100": ("APP_CLOUDS", 1920, 1080, 1.5, {}),
+    "atmosphere1080": ("APP_ATMOSPHERE", 1920, 1080, 1.0, {}),
+    "planet2160": ("APP_PLANET", 3840, 2160, 2.0, {}),
+    "raytracer4320": ("APP_RAYTRACER", 7680, 4320, 1.0, {}),
+    "egg256": ("APP_EGG", 256, 256, 1.0, {}),
+}
+METRIC = "Mpixels/sec at 1920x1080 (APP_CLOUDS)"
+# FP32 lane-instruction cost table for the algorithmic-work estimate (DESIGN.md "Roofline"):
+# SASS instruction counts of the sbx_math.h routines and of the noise_iq body around its 8 hashes.
+COST = {"sin": 40, "cos": 40, "exp": 26, "pow": 60, "sqrt": 8, "other": 60}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation of the path on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_rate(workload, budget_s=15.0, max_parts=None):
+    """Mpix/s of oracle/_ref on all host cores over a bounded sample of rows of the workload frame."""
+    from oracle import loader
+    from shaderbox_b200.abi import Shard, default_params
+
+    app, w, h, t, ov = WORKLOADS[workload]
+    p = default_params(w, h, t, **ov)
+    cores = os.cpu_count() or 1
+    if loader.have_ref_fast():
+        render, kind, build = loader.ref_fast_render, "reference", "oracle/_ref fast build (-O3 -ffast-math -mavx2 -mfma, src/Makefile:12-13 minus -march=native)"
+    elif loader.have_ref():
+        render, kind, build = loader.ref_render, "reference", "oracle/_ref strict build (-O2 -ffp-contract=off)"
+    else:
+        render, kind, build = loader.oracle_render, "port", "oracle/sbx_oracle.c (-O2 strict)"
+    # calibrate on rows spread over the frame (every (h/8)-th row), then size the sample to the budget
+    parts = max(1, h // 8)
+    t0 = time.perf_counter()
+    render(app, p, shard=Shard(1, parts, parts // 2), nthreads=cores)
+    dt = time.perf_counter() - t0
+    rows_cal = len(range(parts // 2, h, parts))
+    per_row = dt / max(1, rows_cal)
+    want_rows = int(max(rows_cal, min(h, budget_s / max(per_row, 1e-9))))
+    parts2 = max(1, h // want_rows)
+    sh = Shard(1, parts2, parts2 // 2)
+    rows = len(range(parts2 // 2, h, parts2))
+    t0 = time.perf_counter()
+    render(app, p, shard=sh, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": rows * w / dt * 1e-6, "unit": "Mpixels/s", "cores": cores, "kind": kind,
+            "sample": "%d of %d rows (every %d-th) of the %dx%d frame, %.1f s, %s" % (rows, h, parts2, w, h, dt, build),
+            "seconds": dt, "rows": rows, "parts": parts2}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    workload = args.workload
+    app, w, h, t, ov = WORKLOADS[workload]
+    # each step is one bounded sample; size it so steps+warmup finish within a few minutes
+    total_budget = 120.0
+    per_step = max(2.0, total_budget / max(1, args.steps + args.warmup))
+    first = cpu_reference_rate(workload, budget_s=per_step)
+    from oracle import loader
+    from shaderbox_b200.abi import Shard, default_params
+
+    render = loader.ref_fast_render if loader.have_ref_fast() else (loader.ref_render if loader.have_ref() else loader.oracle_render)
+    p = default_params(w, h, t, **ov)
+    sh = Shard(1, first["parts"], first["parts"] // 2)
+    cores = first["cores"]
+    for _ in range(max(0, args.warmup - 1)):
+        render(app, p, shard=sh, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        render(app, p, shard=sh, nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = first["rows"] * w * args.steps / dt * 1e-6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * (h / first["rows"]),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s %dx%d u_time=%g %s" % (app, w, h, t, json.dumps(ov)), "host": "CPU, %d threads" % cores,
+                   "ms_per_step_note": "extrapolated to the full frame from the row sample"},
+        "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": cores, "kind": first["kind"], "sample": first["sample"]},
+        "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import shaderbox_b200 as sbx
+    from shaderbox_b200 import multi
+    from shaderbox_b200.abi import default_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- shaderbox_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    app, w, h, t, ov = WORKLOADS[args.workload]
+    p = default_params(w, h, t, **ov)
+    r = sbx.Renderer(app, device=local_rank, variant=args.variant)
+    stripe = args.stripe_rows
+    shard = multi.shard_of(rank, world, stripe)
+    rows = multi.part_rows(h, shard)
+    stream = torch.cuda.current_stream(dev)
+    part = torch.empty((rows, w, 4), dtype=torch.float32, device=dev)
+    frame = torch.empty((h, w, 4), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    launches_per_step = 1 + ((world if rank == 0 else 0) if world > 1 else 0)
+
+    def step():
+        """kernel (+ gather + unshard at N > 1), all on `stream`"""
+        if world == 1:
+            r.render_into(p, part.data_ptr(), shard=shard, stream=stream.cuda_stream)
+        else:
+            multi.render_distributed(r, p, stripe, frame_out=frame, part_out=part)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+        flush.zero_()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                          # evict the previous frame from L2 (untimed)
+        if world > 1:
+            dist.barrier()                     # all ranks start the step together
+        ev[k][0].record(stream)
+        if world == 1:
+            step()
+            ev[k][1].record(stream)
+        else:
+            r.render_into(p, part.data_ptr(), shard=shard, stream=stream.cuda_stream)
+            ev[k][1].record(stream)
+            parts = multi.gather_parts(part, w, h, stripe, 0)
+            if parts is not None:
+                for q, prt in enumerate(parts):
+                    if prt.shape[0]:
+                        r.unshard(w, h, multi.shard_of(q, world, stripe), prt.data_ptr(), frame.data_ptr(), stream=stream.cuda_stream)
+        ev[k][2].record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    kernel_ms = [a.elapsed_time(b) for a, b, _ in ev]
+    step_ms = [a.elapsed_time(c) for a, _, c in ev]
+    clocks = sampler.stop() if rank == 0 else None
+    tm = r.timing()
+
+    # max over ranks of the timed total
+    tot = torch.tensor([sum(step_ms), sum(kernel_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    total_ms, total_kernel_ms = float(tot[0]), float(tot[1])
+
+    # ---- e2e: the reference-facing host call, host buffers, copies inside the timed region --------
+    host = torch.empty((rows, w, 4), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        r.render_host_ptr(p, host.data_ptr(), shard=shard)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        r.render_host_ptr(p, host.data_ptr(), shard=shard)
+    torch.cuda.synchronize(dev)
+    e_local = time.perf_counter() - e0
+    e_t = torch.tensor([e_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e_t[0])
+    checksum = float(host[::97, ::89, :3].double().sum())   # device->host result actually read
+
+    if rank == 0:
+        hbm_peak, sm_max_mhz, peak_src = peaks()
+        px = w * h
+        value = px * args.steps / (total_ms * 1e-3) * 1e-6
+        avg_kernel_ms = total_kernel_ms / args.steps
+        alg_bytes = 16.0 * rows * w                       # this rank's launch: 16 B/pixel written, 0 read
+        achieved = alg_bytes / (avg_kernel_ms * 1e-3) * 1e-9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.workload if world == 1 else "", None)
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s %dx%d u_time=%g %s" % (app, w, h, t, json.dumps(ov)), "variant": tm_variant(r, args),
+                       "l2": "flushed between steps (256 MiB memset on the same stream, outside the timed events); the frame is write-only",
+                       "sharding": "none" if world == 1 else "%d-row stripes round-robin over %d ranks, gather to rank 0 + unshard inside the step" % (stripe, world),
+                       "grid": tm["grid_blocks"], "block": tm["block_threads"], "regs": tm["regs_per_thread"], "ctas_per_sm": tm["blocks_per_sm"]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "sbx_render", "kernel_ms": avg_kernel_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "write-only path: 16 B/pixel out, 0 in; the binding roof is FP32 issue (see fp32_issue)"},
+            "e2e": {"value": px * args.steps / e2e_s * 1e-6, "unit": "Mpixels/s", "h2d_bytes_per_step": sbx_params_bytes(),
+                    "d2h_bytes_per_step": int(16 * rows * w), "checksum": checksum,
+                    "api": "sbx_render_host (C ABI) via shaderbox_b200.Renderer.render_host_ptr, pinned host frame"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
+            "kernel_only": {"ms": avg_kernel_ms, "mpix_s": px / (avg_kernel_ms * 1e-3) * 1e-6 if world == 1 else None},
+        }
+        if world == 1 and not args.no_cpu:
+            cb = cpu_reference_rate(args.workload, budget_s=args.cpu_seconds)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["fp32_issue"] = fp32_issue(args.workload, avg_kernel_ms, sm_max_mhz, clocks)
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def tm_variant(r, args):
+    return args.variant or "default (native if present, else plugin)"
+
+
+def sbx_params_bytes():
+    import ctypes
+
+    from shaderbox_b200.abi import Params
+
+    return ctypes.sizeof(Params)
+
+
+def fp32_issue(workload, kernel_ms, sm_max_mhz, clocks):
+    """Algorithmic FP32 lane-instructions (oracle call counters x COST) / kernel time / issue peak."""
+    from oracle import loader
+    from shaderbox_b200.abi import Shard, default_params
+
+    app, w, h, t, ov = WORKLOADS[workload]
+    if not (loader.have_oracle() and app != "APP_SDF_AO"):
+        return None
+    parts = max(1, h // 16)
+    rows = len(range(parts // 2, h, parts))
+    _, c = loader.oracle_render(app, default_params(w, h, t, **ov), shard=Shard(1, parts, parts // 2), want_counts=True)
+    per_px = {k: v / float(rows * w) for k, v in c.items()}
+    ops_px = sum(per_px[k] * COST[k] for k in COST)
+    noise_px = per_px["sin"] / 8.0 * 74.0 if app in ("APP_CLOUDS", "APP_PLANET") else 0.0
+    alg = (ops_px + noise_px) * w * h
+    clk = (clocks or {}).get("sm_mhz") or sm_max_mhz
+    peak = 148 * 128 * clk * 1e6
+    return {"calls_per_pixel": per_px, "alg_lane_instr_per_frame": alg, "achieved_lane_instr_per_s": alg / (kernel_ms * 1e-3),
+            "peak_lane_instr_per_s": peak, "frac": alg / (kernel_ms * 1e-3) / peak, "clock_mhz_used": clk,
+            "note": "call counts from the oracle on %d sampled rows; cost table in bench.py COST (SASS counts of sbx_math.h); "
+                    "hash(n) calls served by the memo table still count as the reference's sin" % rows}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="clouds1080", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", default=None, help="native | plugin (default: native if present)")
+    ap.add_argument("--stripe-rows", type=int, default=4)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

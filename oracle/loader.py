@@ -16,6 +16,7 @@ from shaderbox_b200.abi import Params, Shard, shard_rows
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libsbx_ref.so")
+REF_FAST_SO = os.path.join(HERE, "_ref", "libsbx_ref_fast.so")   # speed baseline only (fast-math), never parity
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 
 _cache = {}
@@ -29,6 +30,10 @@ def _load(path):
 
 def have_ref():
     return os.path.exists(REF_SO)
+
+
+def have_ref_fast():
+    return os.path.exists(REF_FAST_SO)
 
 
 def have_oracle():
@@ -63,6 +68,29 @@ def ref_render(app, params, shard=None, nthreads=0, want_counts=False):
     return _render(_load(REF_SO), "sbxref", app, params, shard, nthreads, want_counts)
 
 
+def ref_fast_render(app, params, shard=None, nthreads=0, want_counts=False):
+    """The reference's headers with the reference's own (fast-math) build flags: TIMING ONLY."""
+    return _render(_load(REF_FAST_SO), "sbxref", app, params, shard, nthreads, False)
+
+
 def oracle_render(app, params, shard=None, nthreads=0, want_counts=False):
     """The plain-C restatement."""
     return _render(_load(ORACLE_SO), "sbxoracle", app, params, shard, nthreads, want_counts)
+
+
+def ref_eval_op(op, inputs, out_width):
+    """One operator of the reference's own headers on the rows of `inputs` (oracle/ref/ref_ops.cpp);
+    same op names and layouts as sbx_eval_op."""
+    lib = _load(REF_SO)
+    a = np.ascontiguousarray(inputs, dtype=np.float32)
+    if a.ndim == 1:
+        a = a[:, None]
+    out = np.zeros((a.shape[0], out_width), dtype=np.float32)
+    fn = lib.sbxref_eval_op
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    rc = fn(op.encode(), a.ctypes.data_as(C.c_void_p), a.shape[1], out.ctypes.data_as(C.c_void_p), out_width,
+            a.shape[0])
+    if rc != 0:
+        raise RuntimeError("sbxref_eval_op(%s) failed: %d" % (op, rc))
+    return out

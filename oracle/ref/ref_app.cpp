@@ -28,7 +28,11 @@ namespace ref {
 struct counts_t { unsigned long long sin_, cos_, exp_, pow_, sqrt_, other_; };
 static thread_local counts_t tl_counts;
 }
+#ifdef SBX_REF_NO_COUNT   /* timing build: no counter traffic in the inner loops */
+#define GLSL_COUNT(what) ((void)0)
+#else
 #define GLSL_COUNT(what) (++::ref::tl_counts.what)
+#endif
 #include "glsl_shim.h"
 
 namespace ref {

@@ -83,6 +83,7 @@ class Renderer:
         if rc != SBX_OK:
             raise SbxError(rc, "sbx_create", (self._L.sbx_last_error(None) or b"").decode(errors="replace"))
         self.app = None
+        self.device = int(device)
         self.load_app(app, variant)
 
     def _check(self, rc, where):

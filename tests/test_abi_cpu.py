@@ -1,0 +1,150 @@
+"""CPU: the C-ABI library loads, exports what include/sbx.h declares, and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import shaderbox_b200 as sbx
+from shaderbox_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sbx.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sbx_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = sbx.lib()
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "libsbx.so does not export " + n
+    assert set(names) == set(sbx.EXPORTS)
+
+
+def test_no_oracle_or_torch_linked_into_product():
+    out = subprocess.run(["ldd", sbx.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "torch" not in out and "libsbx_ref" not in out
+    syms = subprocess.run(["nm", "-D", sbx.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sbxoracle" not in syms and "sbxref" not in syms
+
+
+def test_default_params_match_reference_uniform_defaults():
+    # src/uniform_buffer.h:41-58
+    lib = sbx.lib()
+    p = abi.Params()
+    assert lib.sbx_default_params(C.byref(p), 1920, 1080) == 0
+    q = abi.default_params(1920, 1080)
+    assert bytes(p) == bytes(q)
+    assert (p.width, p.height, p.cld_march_steps, p.illum_march_steps) == (1920, 1080, 100, 6)
+    assert np.allclose(list(p.wind_dir), [0, 0, 0.2]) and np.allclose(list(p.sun_color), [1, 0.7, 0.55])
+    assert np.isclose(p.sigma_scattering, 0.15) and np.isclose(p.cld_coverage, 0.535) and p.cld_thick == 125.0
+    assert p.atm_radius == 5000.0 and p.atm_ground_y == 4750.0
+    assert np.isclose(p.fog_density, 0.1) and p.fog_falloff == 0.5
+    assert lib.sbx_default_params(None, 4, 4) == abi.SBX_ERR_INVALID
+    assert lib.sbx_default_params(C.byref(p), 0, 4) == abi.SBX_ERR_INVALID
+
+
+@pytest.mark.parametrize("height", [1, 3, 4, 7, 45, 1080, 2160])
+def test_shard_rows_agree_with_python_twin(height):
+    lib = sbx.lib()
+    for stripe in (1, 2, 4, 7):
+        for parts in (1, 2, 3, 8):
+            total = 0
+            for part in range(parts):
+                sh = abi.Shard(stripe, parts, part)
+                n = lib.sbx_shard_rows(C.byref(sh), height)
+                assert n == len(abi.shard_rows(stripe, parts, part, height))
+                total += n
+            assert total == height
+    bad = abi.Shard(4, 2, 2)
+    assert lib.sbx_shard_rows(C.byref(bad), height) == abi.SBX_ERR_INVALID
+
+
+def test_error_strings_and_version():
+    lib = sbx.lib()
+    assert lib.sbx_strerror(0) == b"ok"
+    for code in range(-7, 0):
+        assert lib.sbx_strerror(code) not in (b"", b"unknown status")
+    assert b"sm_100a" in lib.sbx_version()
+
+
+def test_invalid_arguments_are_rejected_without_a_context():
+    lib = sbx.lib()
+    p = abi.default_params(8, 8)
+    buf = np.zeros((8, 8, 4), np.float32)
+    assert lib.sbx_render_host(None, C.byref(p), None, buf.ctypes.data_as(C.c_void_p)) == abi.SBX_ERR_INVALID
+    assert lib.sbx_render_device(None, C.byref(p), None, None, None) == abi.SBX_ERR_INVALID
+    assert lib.sbx_load_app(None, b"APP_EGG", None) == abi.SBX_ERR_INVALID
+    assert lib.sbx_create(0, None) == abi.SBX_ERR_INVALID
+
+
+def test_no_cpu_path_without_a_device():
+    """On a machine without a B200 the product must refuse, not fall back."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    with pytest.raises(sbx.SbxError) as e:
+        sbx.Renderer("APP_CLOUDS")
+    assert e.value.status == abi.SBX_ERR_NO_DEVICE
+
+
+MINI_APP = r"""
+// a user-written app in the shaderbox plugin contract (src/main.h:3,35-50): camera, scene, render, FOV
+#include "def.h"
+#include "util.h"
+#include "intersect.h"
+#include "noise_iq.h"
+#include "fbm.h"
+DECL_FBM_FUNC(fbm, 3, noise_iq(p))
+_mutable(float) seen = 0.;
+void setup_camera(_inout(vec3) eye, _inout(vec3) look_at) { eye = vec3(0, 0, 3.); look_at = vec3(0, 0, 0); }
+void setup_scene() { seen = 1.; }
+vec3 render(_in(ray_t) ray, _in(vec3) point_cam)
+{
+    _constant(sphere_t) s = _begin(sphere_t) vec3(0, 0, 0), 1., 0 _end;
+    hit_t hit = no_hit;
+    intersect_sphere(ray, s, hit);
+    if (hit.t >= max_dist) return vec3(.1, .2, .3) * seen;
+    return vec3(fbm(hit.origin * 4. + u_time, 2., .5, .5));
+}
+#define FOV tan(radians(30.))
+#include "main.h"
+"""
+
+
+def test_plugin_contract_compiles_without_a_gpu(tmp_path):
+    """sbx_compile_app: an unchanged app header -> sm_100a cubin via NVRTC (no GPU needed)."""
+    hdr = tmp_path / "app_mini.h"
+    hdr.write_text(MINI_APP)
+    img = tmp_path / "APP_MINI.plugin.cubin"
+    sbx.compile_app(str(hdr), "APP_MINI", str(img))
+    blob = img.read_bytes()
+    assert blob[:4] == b"\x7fELF" and len(blob) > 4096
+    dump = subprocess.run(["cuobjdump", "-elf", str(img)], capture_output=True, text=True).stdout
+    assert "sm_100" in dump or "EF_CUDA_SM100" in dump
+    assert "sbx_render" in dump
+
+
+def test_compile_errors_are_reported_not_swallowed(tmp_path):
+    hdr = tmp_path / "app_bad.h"
+    hdr.write_text(MINI_APP.replace("return vec3(fbm(", "return vec3(no_such_function("))
+    with pytest.raises(sbx.SbxError) as e:
+        sbx.compile_app(str(hdr), "APP_BAD", str(tmp_path / "bad.cubin"))
+    assert e.value.status == abi.SBX_ERR_COMPILE and "no_such_function" in str(e.value)
+
+
+def test_prebuilt_kernel_images_are_sm100a_and_present():
+    img_dir = os.path.join(ROOT, "shaderbox_b200", "images")
+    for app in sbx.APPS:
+        path = os.path.join(img_dir, app + ".plugin.cubin")
+        assert os.path.exists(path), path + " missing: run __graft_entry__.build()"
+    assert os.path.exists(os.path.join(img_dir, "sbx_util.cubin"))

@@ -1,0 +1,63 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic (stripe sharding, the single gather, reassembly).
+
+The parts are produced by the CPU oracle here (the checker standing in for the renderer in a test);
+on the GPU box the same functions move CUDA tensors over NCCL (test_gpu_parity.py, bench.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import loader
+from shaderbox_b200 import multi
+from shaderbox_b200.abi import Shard, default_params
+from util import bits_equal
+
+APP, W, H, T = "APP_PLANET", 40, 23, 2.0   # 23 rows: ragged against every stripe size used below
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, stripe, result_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p = default_params(W, H, T)
+        sh = multi.shard_of(rank, world, stripe)
+        part = torch.from_numpy(loader.oracle_render(APP, p, shard=Shard(*sh), nthreads=1))
+        assert part.shape[0] == multi.part_rows(H, sh)
+        parts = multi.gather_parts(part, W, H, stripe, dst=0)
+        if rank == 0:
+            frame = multi.assemble_rows(parts, W, H, stripe)
+            np.save(result_path, frame.numpy())
+        else:
+            assert parts is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,stripe", [(2, 4), (2, 1), (3, 5)])
+def test_gathered_frame_is_bit_identical_to_single_rank(tmp_path, world, stripe):
+    result = str(tmp_path / "frame.npy")
+    mp.spawn(_worker, args=(world, _free_port(), stripe, result), nprocs=world, join=True)
+    full = loader.oracle_render(APP, default_params(W, H, T))
+    assert bits_equal(np.load(result), full)
+
+
+def test_single_rank_is_identity():
+    p = default_params(W, H, T)
+    full = torch.from_numpy(loader.oracle_render(APP, p))
+    assert multi.part_rows(H, multi.shard_of(0, 1)) == H
+    out = multi.assemble_rows([full], W, H, 4)
+    assert bits_equal(out.numpy(), full.numpy())
