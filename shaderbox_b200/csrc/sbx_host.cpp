@@ -143,7 +143,7 @@ struct sbx_ctx {
     CUfunction k_hash = nullptr, k_unshard = nullptr, k_eval = nullptr;
 
     CUdeviceptr lut = 0;          // SBX_LUT_MATH_BYTES
-    CUdeviceptr hash_tab = 0;     // floats
+    CUdeviceptr hash_tab = 0;     // float4 entries
     int hash_lo = 0, hash_len = 0;
     int opt_hash_log2 = 18;       // table covers [-2^(k-1), 2^(k-1))
     int opt_use_hash = 1;
@@ -196,7 +196,7 @@ int load_util(sbx_ctx* ctx) {
 }
 
 // LUT block + lattice-hash memo; (re)built when the table option changes
-int ensure_tables(sbx_ctx* ctx, CUstream stream) {
+int ensure_tables(sbx_ctx* ctx, CUstream stream, bool force_table = false) {
     int st = load_util(ctx);
     if (st != SBX_OK) return st;
     if (!ctx->lut) {
@@ -208,12 +208,13 @@ int ensure_tables(sbx_ctx* ctx, CUstream stream) {
         SBX_TRY(ctx->cu->MemAlloc(&ctx->lut, SBX_LUT_MATH_BYTES), "cuMemAlloc(lut)");
         SBX_TRY(ctx->cu->MemcpyHtoD(ctx->lut, block, SBX_LUT_MATH_BYTES), "cuMemcpyHtoD(lut)");
     }
-    const int want_len = ctx->opt_use_hash ? (1 << ctx->opt_hash_log2) : 0;
+    // hand-written kernels index the memo table unconditionally (misses are detected, not avoided)
+    const int want_len = (ctx->opt_use_hash || force_table) ? (1 << ctx->opt_hash_log2) : 0;
     if (want_len != ctx->hash_len) {
         if (ctx->hash_tab) { ctx->cu->StreamSynchronize(stream); ctx->cu->MemFree(ctx->hash_tab); ctx->hash_tab = 0; }
         ctx->hash_len = 0;
         if (want_len > 0) {
-            SBX_TRY(ctx->cu->MemAlloc(&ctx->hash_tab, (size_t)want_len * sizeof(float)), "cuMemAlloc(hash table)");
+            SBX_TRY(ctx->cu->MemAlloc(&ctx->hash_tab, (size_t)want_len * 4 * sizeof(float)), "cuMemAlloc(hash table)");
             int lo = -(want_len / 2), len = want_len;
             void* args[] = {&ctx->hash_tab, &lo, &len, &ctx->lut};
             SBX_TRY(ctx->cu->LaunchKernel(ctx->k_hash, (unsigned)((len + 255) / 256), 1, 1, 256, 1, 1,
@@ -444,7 +445,7 @@ int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard,
     CUstream stream = (CUstream)stream_;
     ctx_scope scope(ctx);
     ctx->timing.launches = 0;
-    int st = ensure_tables(ctx, stream);
+    int st = ensure_tables(ctx, stream, ctx->current->variant != "plugin");
     if (st != SBX_OK) return st;
 
     sbx_launch L;
@@ -458,10 +459,10 @@ int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard,
     L.tiles_x = (p->width + SBX_TILE_W - 1) / SBX_TILE_W;
     L.tiles_y = (L.local_rows + SBX_TILE_H - 1) / SBX_TILE_H;
     L.out = dev_rgba;
-    L.hash_tab = (const float*)ctx->hash_tab;
+    L.hash_tab = (const float4*)ctx->hash_tab;
     L.hash_bias = SBX_HASH_MAGIC_BITS + ctx->hash_lo;
     L.hash_len = ctx->hash_len;
-    L.hash_span = ctx->hash_len > 271 ? ctx->hash_len - 271 : 0;
+    L.hash_span = ctx->hash_len > 113 ? ctx->hash_len - 113 : 0;
     L.lut = (const void*)ctx->lut;
 
     kernel_image* img = ctx->current;
@@ -573,10 +574,10 @@ int sbx_eval_op(sbx_ctx* ctx, const char* op, const float* in, int in_stride, fl
     sbx_launch L;
     std::memset(&L, 0, sizeof L);
     sbx_default_params(&L.p, 1, 1);
-    L.hash_tab = (const float*)ctx->hash_tab;
+    L.hash_tab = (const float4*)ctx->hash_tab;
     L.hash_bias = SBX_HASH_MAGIC_BITS + ctx->hash_lo;
     L.hash_len = ctx->hash_len;
-    L.hash_span = ctx->hash_len > 271 ? ctx->hash_len - 271 : 0;
+    L.hash_span = ctx->hash_len > 113 ? ctx->hash_len - 113 : 0;
     L.lut = (const void*)ctx->lut;
     int rc = SBX_OK;
     do {

@@ -14,14 +14,18 @@ __device__ __forceinline__ void sbx_util_stage_lut(const void* lut_global) {
     __syncthreads();
 }
 
-// hash_tab[k] = fract(sin(float(lo + k)) * 753.5453123)   (src/noise_iq.h:5-9)
-extern "C" __global__ void sbx_hash_table_kernel(float* tab, int lo, int len, const void* lut) {
+// hash(n) = fract(sin(n) * 753.5453123)   (src/noise_iq.h:5-9)
+__device__ __forceinline__ float sbx_hash_of(float n) {
+    const float s = sbx_sinf(n) * 753.5453123f;
+    return s - floorf(s);
+}
+// tab[k] = { h(n), h(n+1), h(n+157), h(n+158) }, n = lo + k: one z-slice of a noise_iq cell per entry
+extern "C" __global__ void sbx_hash_table_kernel(float4* tab, int lo, int len, const void* lut) {
     sbx_util_stage_lut(lut);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= len) return;
     const float n = (float)(lo + k);
-    const float s = sbx_sinf(n) * 753.5453123f;
-    tab[k] = s - floorf(s);
+    tab[k] = make_float4(sbx_hash_of(n), sbx_hash_of(n + 1.0f), sbx_hash_of(n + 157.0f), sbx_hash_of(n + 158.0f));
 }
 
 // part -> frame: local row lr of shard (stripe, parts, part) is frame row y

@@ -3,10 +3,12 @@
 // The reference hashes a lattice index with fract(sin(n)*753.5453123) -- 8 sines per noise call,
 // >95 % of APP_CLOUDS' work.  The lattice index n = px + 157 py + 113 pz is
 // always an INTEGER-valued float (floor() results, integer weights; rounding an integer to fp32
-// still yields an integer), so hash(n) is memoised: sbx_L->hash_tab[k] holds hash(hash_lo + k),
-// filled on the device by sbx_hash_table_kernel with this very function's arithmetic, and the
-// eight corners become eight read-only loads off one base address.  Lattice indices outside the
-// table take the arithmetic path, so results are bit-identical either way.
+// still yields an integer), so hash(n) is memoised.  The table is laid out for the access pattern
+// of noise_iq: entry k is the float4 { h(n), h(n+1), h(n+157), h(n+158) } with n = hash_lo + k --
+// one z-slice of the cell -- so the eight corners are TWO 16-byte read-only loads (entries k and
+// k+113) instead of eight 4-byte ones.  It is filled on the device by sbx_hash_table_kernel with
+// this very file's arithmetic; lattice indices outside the table take the arithmetic path, so
+// results are bit-identical either way.
 
 // arithmetic definition (src/noise_iq.h:5-9); out of line: it is the rare path once the memo
 // table is in place, and eight inlined copies per noise call would only bloat the hot loop
@@ -16,24 +18,24 @@ SBX_FN float hash(_in(float) n) {
     // (n + 1.5*2^23) - 1.5*2^23 == n  <=>  n is an integer with |n| < 2^22
     const float shifted = n + 12582912.0f;
     const unsigned k = (unsigned)(__float_as_int(shifted) - sbx_L->hash_bias);
-    if (k < (unsigned)sbx_L->hash_len && (shifted - 12582912.0f) == n) return __ldg(sbx_L->hash_tab + k);
+    if (k < (unsigned)sbx_L->hash_len && (shifted - 12582912.0f) == n) return __ldg(&sbx_L->hash_tab[k].x);
     return sbx_hash_arith(n);
 }
 
 SBX_FN float noise_iq(_in(vec3) x) {
     const vec3 p = floor(x);
     vec3 f = fract(x);
-    f = f * f * (3.0f - 2.0f * f);                       // smoothstep weights
+    // smoothstep weights f*f*(3 - 2f): 2f is exact, so fma(f, -2, 3) rounds exactly like 3 - 2f
+    f = vec3(f.x * f.x * __fmaf_rn(f.x, -2.0f, 3.0f), f.y * f.y * __fmaf_rn(f.y, -2.0f, 3.0f),
+             f.z * f.z * __fmaf_rn(f.z, -2.0f, 3.0f));
 
     const float n = p.x + p.y * 157.0f + 113.0f * p.z;   // lattice index, stride (1, 157, 113)
     float h000, h100, h010, h110, h001, h101, h011, h111;
     const unsigned k = (unsigned)(__float_as_int(n + 12582912.0f) - sbx_L->hash_bias);
-    if (k < (unsigned)sbx_L->hash_span) {                // all 8 corners k .. k+271 are tabulated
-        const float* __restrict__ t = sbx_L->hash_tab + k;
-        h000 = __ldg(t);       h100 = __ldg(t + 1);
-        h010 = __ldg(t + 157); h110 = __ldg(t + 158);
-        h001 = __ldg(t + 113); h101 = __ldg(t + 114);
-        h011 = __ldg(t + 270); h111 = __ldg(t + 271);
+    if (k < (unsigned)sbx_L->hash_span) {                // entries k and k+113 are tabulated
+        const float4 z0 = __ldg(sbx_L->hash_tab + k), z1 = __ldg(sbx_L->hash_tab + k + 113);
+        h000 = z0.x; h100 = z0.y; h010 = z0.z; h110 = z0.w;
+        h001 = z1.x; h101 = z1.y; h011 = z1.z; h111 = z1.w;
     } else {
         h000 = sbx_hash_arith(n + 0.0f);   h100 = sbx_hash_arith(n + 1.0f);
         h010 = sbx_hash_arith(n + 157.0f); h110 = sbx_hash_arith(n + 158.0f);

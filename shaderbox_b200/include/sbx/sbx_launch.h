@@ -2,6 +2,9 @@
 #ifndef SBX_LAUNCH_H_
 #define SBX_LAUNCH_H_
 #include "sbx.h"
+#if !defined(__CUDACC__) && !defined(__CUDACC_RTC__)
+#include <vector_types.h>   /* float4 for the host launcher */
+#endif
 
 #define SBX_TILE_W 8          /* a warp renders an 8 x 4 pixel tile */
 #define SBX_TILE_H 4
@@ -14,11 +17,12 @@ typedef struct sbx_launch {
     int local_rows;             /* rows rendered by this launch */
     int tiles_x, tiles_y;       /* warp tiles covering width x local_rows */
     float* out;                 /* local_rows * width float4, compacted */
-    /* memoised lattice hash (noise_iq.h): hash_tab[k] = hash(hash_lo + k), 0 <= k < hash_len */
-    const float* hash_tab;
+    /* memoised lattice hash (noise_iq.h): hash_tab[k] = { h(n), h(n+1), h(n+157), h(n+158) },
+       n = hash_lo + k, 0 <= k < hash_len */
+    const float4* hash_tab;
     int hash_bias;              /* SBX_HASH_MAGIC_BITS + hash_lo */
     int hash_len;
-    int hash_span;              /* hash_len - 271: largest base index whose 8 corners are all tabulated */
+    int hash_span;              /* hash_len - 113: base indices k whose second z-slice k+113 is tabulated too */
     int pad0;
     const void* lut;            /* SBX_LUT_MATH_BYTES of exp2/log2 tables in global memory (sbx_math.h) */
 } sbx_launch;

@@ -88,6 +88,20 @@ def test_operator_large_seeded_run_vs_oracle_ref(op, renderers):
     assert bits_equal(got, want), op + ": " + diff_report(got, want)
 
 
+@pytest.mark.parametrize("ov", [
+    {}, {"cld_march_steps": 128}, {"cld_coverage": 0.3}, {"cld_coverage": 0.75}, {"cld_coverage": 0.999},
+    {"cld_coverage": 0.0}, {"illum_march_steps": 1, "cld_march_steps": 17}, {"sigma_scattering": 0.9, "cld_thick": 300.0},
+    {"sun_dir": (0.0, 1.0, 0.0), "sun_power": 3.0}, {"u_mouse": (200.0, 0.0, 0.0, 0.0)},
+])
+def test_native_clouds_kernel_matches_oracle_over_the_uniform_space(ov, renderers):
+    """The hand-written CLOUDS kernel skips work it can prove irrelevant (lazy octaves); the proof
+    must hold for every uniform setting, not only the defaults."""
+    w, h, t = 192, 108, 2.5
+    want = loader.oracle_render("APP_CLOUDS", abi.default_params(w, h, t, **ov))
+    check(renderers("APP_CLOUDS", "native").render(w, h, u_time=t, **ov), want)
+    check(renderers("APP_CLOUDS", "plugin").render(w, h, u_time=t, **ov), want)
+
+
 def test_hash_memo_table_is_bit_identical_to_arithmetic(renderers):
     """noise_iq.h memoises hash(n) for integer n; rendering with and without the table must agree."""
     r = renderers("APP_CLOUDS", "plugin")
