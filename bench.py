@@ -54,55 +54,67 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled
+    every 5 ms from a thread (the nvidia-smi -lms recipe needs longer to start than a short run lasts)."""
 
     def __init__(self, device):
         self.device = device
-        self.proc = None
-        self.lines = []
+        self.samples = []          # (t, sm_mhz, power_w, reasons_bitmask)
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
+        self.marks = [None, None]
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES-free boxes: index == CUDA ordinal on the gpurun boxes
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:   # noqa: BLE001
+            self.err = repr(e)
+            self.nv = None
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:   # noqa: BLE001
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), mhz, pw, rs))
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(0.005)
+
+    def mark(self, which):
+        self.marks[which] = time.perf_counter()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no NVML samples: " + getattr(self, "err", "")]}
+        t0, t1 = self.marks
+        timed = [x for x in self.samples if t0 is not None and t1 is not None and t0 <= x[0] <= t1] or self.samples
+        mhz = sorted(x[1] for x in timed)
+        bits = 0
+        for x in timed:
+            bits |= x[3]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "power_w_max": max(x[2] for x in timed),
+                "samples": len(timed), "reasons": sorted(v for k, v in names.items() if bits & k)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -225,17 +237,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)   # runs through warm-up + the timed region (nvidia-smi needs ~0.3 s to start)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
         flush.zero_()
     barrier()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     barrier()
+    sampler.mark(0)
     wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                          # evict the previous frame from L2 (untimed)
@@ -256,6 +268,7 @@ def run_ours(args):
         ev[k][2].record(stream)
     barrier()
     wall = time.perf_counter() - wall0
+    sampler.mark(1)
     kernel_ms = [a.elapsed_time(b) for a, b, _ in ev]
     step_ms = [a.elapsed_time(c) for a, _, c in ev]
     clocks = sampler.stop() if rank == 0 else None
@@ -269,6 +282,8 @@ def run_ours(args):
 
     # ---- e2e: the reference-facing host call, host buffers, copies inside the timed region --------
     host = torch.empty((rows, w, 4), dtype=torch.float32).pin_memory()
+    if args.no_zero_copy:
+        r.set_option("host_zero_copy", 0)
     for _ in range(2):
         r.render_host_ptr(p, host.data_ptr(), shard=shard)
     barrier()
@@ -282,6 +297,7 @@ def run_ours(args):
         dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e_t[0])
     checksum = float(host[::97, ::89, :3].double().sum())   # device->host result actually read
+    zero_copy = bool(r.timing()["zero_copy"])
 
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_src = peaks()
@@ -308,7 +324,9 @@ def run_ours(args):
                          "note": "write-only path: 16 B/pixel out, 0 in; the binding roof is FP32 issue (see fp32_issue)"},
             "e2e": {"value": px * args.steps / e2e_s * 1e-6, "unit": "Mpixels/s", "h2d_bytes_per_step": sbx_params_bytes(),
                     "d2h_bytes_per_step": int(16 * rows * w), "checksum": checksum,
-                    "api": "sbx_render_host (C ABI) via shaderbox_b200.Renderer.render_host_ptr, pinned host frame"},
+                    "api": "sbx_render_host (C ABI) via shaderbox_b200.Renderer.render_host_ptr, pinned host frame",
+                    "d2h": "kernel stores straight into the pinned+mapped host frame (zero-copy over PCIe)" if zero_copy
+                           else "frame rendered in HBM, then cuMemcpyDtoHAsync"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
@@ -372,6 +390,7 @@ def main():
     ap.add_argument("--stripe-rows", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-zero-copy", action="store_true", help="e2e: render in HBM and copy instead of storing into the host frame")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

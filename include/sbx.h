@@ -79,6 +79,7 @@ typedef struct sbx_timing {
     float d2h_ms;        /* frame read-back, if the call had a host destination */
     int   launches;      /* kernels launched by the last call */
     int   grid_blocks, block_threads, regs_per_thread, blocks_per_sm;
+    int   zero_copy;     /* 1 if sbx_render_host stored straight into a pinned+mapped host frame */
 } sbx_timing;
 
 typedef struct sbx_ctx sbx_ctx;
@@ -112,8 +113,10 @@ int sbx_shard_rows(const sbx_shard* shard, int height);
 int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
                       float* dev_rgba, void* stream);
 
-/* Render and copy to HOST memory (host_rgba: rows*width*4 floats).  Synchronous; this is the call
- * the reference-facing hosts make (one frame in, one frame out). */
+/* Render to HOST memory (host_rgba: rows*width*4 floats).  Synchronous; this is the call the
+ * reference-facing hosts make (one frame in, one frame out).  If host_rgba is pinned and mapped
+ * (cudaHostAlloc, a pinned torch tensor) the kernel stores into it directly over PCIe; otherwise the
+ * frame is rendered in HBM and copied. */
 int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
                     float* host_rgba);
 
@@ -122,7 +125,7 @@ int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or
 int sbx_unshard_device(sbx_ctx* ctx, int width, int height, const sbx_shard* shard,
                        const float* dev_part, float* dev_frame, void* stream);
 
-/* Kernel-launch tuning knobs (0 = library default): pixels tile w/h per warp, hash-table size. */
+/* Options: "use_hash_table" 0|1, "hash_table_log2" 9..22 (noise_iq memo table), "host_zero_copy" 0|1. */
 int sbx_set_option(sbx_ctx* ctx, const char* key, int value);
 
 int sbx_last_timing(sbx_ctx* ctx, sbx_timing* out);

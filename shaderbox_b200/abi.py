@@ -56,6 +56,7 @@ class Timing(C.Structure):
         ("block_threads", C.c_int),
         ("regs_per_thread", C.c_int),
         ("blocks_per_sm", C.c_int),
+        ("zero_copy", C.c_int),
     ]
 
 

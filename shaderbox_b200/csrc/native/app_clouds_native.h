@@ -23,7 +23,8 @@
 //  * the Henyey-Greenstein factor of illuminate_volume (:121) depends only on the ray, not on the
 //    sample: one pow per ray instead of one per in-cloud step.
 //  * table misses are deferred: lattice indices are clamped into the memo table and the largest
-//    one is tracked; only if it was out of range is the sample recomputed on the arithmetic path.
+//    one is tracked; only a pixel that ever went out of range is recomputed, on the generic path
+//    (no calls and no miss branches inside the march loops).
 #include "def.h"
 #include "util.h"
 #include "intersect.h"
@@ -41,8 +42,10 @@ float sbx_cov;         // 1 - cld_coverage (:83)
 // z-slice memo of the last fully evaluated sample: position x/y it was taken at and, per octave,
 // the lattice z and the two bilinear slice values
 float sbx_mx, sbx_my;
-float sbx_mz[4], sbx_y0[4], sbx_y1[4];
-unsigned sbx_kmax;     // largest (clamped) table index seen by the current sample
+float sbx_mz0, sbx_mz1, sbx_mz2, sbx_mz3;
+float sbx_a0, sbx_a1, sbx_a2, sbx_a3;   // y0 of octave 0..3
+float sbx_b0, sbx_b1, sbx_b2, sbx_b3;   // y1 of octave 0..3
+unsigned sbx_kmax;     // largest table index this pixel asked for (see render)
 
 SBX_FN void setup_camera(_inout(vec3) eye, _inout(vec3) look_at) {   // :23-30
     eye = vec3(0.0f, -.5f, 0.0f);
@@ -62,8 +65,10 @@ SBX_FN vec3 render_sky_color(_in(vec3) eye_dir) {   // :36-46
 
 SBX_FN float sbx_weight(float f) { return f * f * __fmaf_rn(f, -2.0f, 3.0f); }   // f*f*(3 - 2f), noise_iq.h:16
 
-// one octave of noise_iq (src/noise_iq.h:11-23) evaluated in full; leaves its z-slices in the memo
-SBX_FN float octave_full(_in(vec3) x, const int o) {
+// one octave of noise_iq (src/noise_iq.h:11-23) evaluated in full; returns its two z-slices too.
+// The lattice index is clamped into the memo table and the largest one remembered: a pixel that
+// ever asked for an entry outside the table is recomputed on the generic path (render()).
+SBX_FN float octave_full(_in(vec3) x, float& mz, float& y0, float& y1) {
     const vec3 p = floor(x);
     const float wx = sbx_weight(x.x - p.x), wy = sbx_weight(x.y - p.y), wz = sbx_weight(x.z - p.z);
     const float n = p.x + p.y * 157.0f + 113.0f * p.z;
@@ -71,25 +76,13 @@ SBX_FN float octave_full(_in(vec3) x, const int o) {
     sbx_kmax = ::max(sbx_kmax, k);
     const float4* __restrict__ e = sbx_L->hash_tab + ::min(k, (unsigned)sbx_L->hash_span - 1u);
     const float4 z0 = __ldg(e), z1 = __ldg(e + 113);
-    const float y0 = mix(mix(z0.x, z0.y, wx), mix(z0.z, z0.w, wx), wy);
-    const float y1 = mix(mix(z1.x, z1.y, wx), mix(z1.z, z1.w, wx), wy);
-    sbx_mz[o] = p.z; sbx_y0[o] = y0; sbx_y1[o] = y1;
+    y0 = mix(mix(z0.x, z0.y, wx), mix(z0.z, z0.w, wx), wy);
+    y1 = mix(mix(z1.x, z1.y, wx), mix(z1.z, z1.w, wx), wy);
+    mz = p.z;
     return mix(y0, y1, wz);
 }
 
-// the same octave when x.x, x.y are bit-identical to the memoised sample: only z is new
-SBX_FN float octave_z(_in(vec3) x, const int o) {
-    const float pz = floor(x.z);
-    if (pz != sbx_mz[o]) return octave_full(x, o);
-    return mix(sbx_y0[o], sbx_y1[o], sbx_weight(x.z - pz));
-}
-
 SBX_FN float sbx_density_of(float shape) { return shape * smoothstep(sbx_cov, sbx_cov + .0135f, shape); }   // :83-84
-SBX_FN bool sbx_table_missed() { return sbx_kmax >= (unsigned)sbx_L->hash_span || sbx_L->hash_span <= 0; }
-static __device__ __noinline__ float sbx_density_generic(sbx_app* self, float x, float y, float z) {
-    const vec3 pos = vec3(x, y, z) * cld_noise_factor;
-    return self->sbx_density_of(self->fbm(pos * 2.03f, 2.64f, .5f, .5f));
-}
 
 // density_func (:62-86) for a view-march sample: fbm(pos * 2.03, 2.64, .5, .5) of src/fbm.h:6
 // unrolled (H = .5 .25 .125 .0625) with the lazy-octave exits
@@ -97,47 +90,44 @@ SBX_FN float density_view(_in(vec3) pos_in) {
     const vec3 pos = pos_in * cld_noise_factor;
     vec3 p = pos * 2.03f;
     const float guard = 1e-5f;
-    sbx_kmax = 0u;
     sbx_mx = pos_in.x; sbx_my = pos_in.y;
-    float t = octave_full(p, 0) * .5f;                   // 0 + n*.5 == n*.5 (n >= +0)
-    if (t <= sbx_cov - .4375f - guard) { sbx_mx = __int_as_float(0x7fc00000); return sbx_table_missed() ? sbx_density_generic(this, pos_in.x, pos_in.y, pos_in.z) : 0.0f; }
+    float t = octave_full(p, sbx_mz0, sbx_a0, sbx_b0) * .5f;      // 0 + n*.5 == n*.5 (n >= +0)
+    if (t <= sbx_cov - .4375f - guard) return 0.0f;
     p *= 2.64f;
-    t += octave_full(p, 1) * .25f;
-    if (t <= sbx_cov - .1875f - guard) { sbx_mx = __int_as_float(0x7fc00000); return sbx_table_missed() ? sbx_density_generic(this, pos_in.x, pos_in.y, pos_in.z) : 0.0f; }
+    t += octave_full(p, sbx_mz1, sbx_a1, sbx_b1) * .25f;
+    if (t <= sbx_cov - .1875f - guard) return 0.0f;
     p *= 2.64f;
-    t += octave_full(p, 2) * .125f;
-    if (t <= sbx_cov - .0625f - guard) { sbx_mx = __int_as_float(0x7fc00000); return sbx_table_missed() ? sbx_density_generic(this, pos_in.x, pos_in.y, pos_in.z) : 0.0f; }
+    t += octave_full(p, sbx_mz2, sbx_a2, sbx_b2) * .125f;
+    if (t <= sbx_cov - .0625f - guard) return 0.0f;
     p *= 2.64f;
-    t += octave_full(p, 3) * .0625f;
-    if (sbx_table_missed()) { sbx_mx = __int_as_float(0x7fc00000); return sbx_density_generic(this, pos_in.x, pos_in.y, pos_in.z); }
+    t += octave_full(p, sbx_mz3, sbx_a3, sbx_b3) * .0625f;
     return sbx_density_of(t);
 }
 
-// density_func for a light-march sample: z-slice reuse when x and y are those of the memoised sample
+// density_func for a light-march sample.  If x and y are bit-identical to the memoised sample and
+// every octave stays in its lattice cell along z, each octave is one weight and one mix.
 SBX_FN float density_light(_in(vec3) pos_in) {
-    const vec3 pos = pos_in * cld_noise_factor;
-    vec3 p = pos * 2.03f;
-    sbx_kmax = 0u;
+    const float z0 = pos_in.z * cld_noise_factor * 2.03f;         // the z chain of p = pos*.001*2.03, p *= 2.64
+    const float z1 = z0 * 2.64f, z2 = z1 * 2.64f, z3 = z2 * 2.64f;
+    const float c0 = floor(z0), c1 = floor(z1), c2 = floor(z2), c3 = floor(z3);
     float t;
-    if (pos_in.x == sbx_mx && pos_in.y == sbx_my) {
-        t = octave_z(p, 0) * .5f;
-        p *= 2.64f;
-        t += octave_z(p, 1) * .25f;
-        p *= 2.64f;
-        t += octave_z(p, 2) * .125f;
-        p *= 2.64f;
-        t += octave_z(p, 3) * .0625f;
+    if (pos_in.x == sbx_mx && pos_in.y == sbx_my && c0 == sbx_mz0 && c1 == sbx_mz1 && c2 == sbx_mz2 && c3 == sbx_mz3) {
+        t = mix(sbx_a0, sbx_b0, sbx_weight(z0 - c0)) * .5f;
+        t += mix(sbx_a1, sbx_b1, sbx_weight(z1 - c1)) * .25f;
+        t += mix(sbx_a2, sbx_b2, sbx_weight(z2 - c2)) * .125f;
+        t += mix(sbx_a3, sbx_b3, sbx_weight(z3 - c3)) * .0625f;
     } else {
+        const vec3 pos = pos_in * cld_noise_factor;
+        vec3 p = pos * 2.03f;
         sbx_mx = pos_in.x; sbx_my = pos_in.y;
-        t = octave_full(p, 0) * .5f;
+        t = octave_full(p, sbx_mz0, sbx_a0, sbx_b0) * .5f;
         p *= 2.64f;
-        t += octave_full(p, 1) * .25f;
+        t += octave_full(p, sbx_mz1, sbx_a1, sbx_b1) * .25f;
         p *= 2.64f;
-        t += octave_full(p, 2) * .125f;
+        t += octave_full(p, sbx_mz2, sbx_a2, sbx_b2) * .125f;
         p *= 2.64f;
-        t += octave_full(p, 3) * .0625f;
+        t += octave_full(p, sbx_mz3, sbx_a3, sbx_b3) * .0625f;
     }
-    if (sbx_table_missed()) { sbx_mx = __int_as_float(0x7fc00000); return sbx_density_generic(this, pos_in.x, pos_in.y, pos_in.z); }
     return sbx_density_of(t);
 }
 
@@ -182,10 +172,65 @@ SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-202
     return vec4(cloud.radiance, cloud.alpha * smoothstep(.0f, .2f, cutoff));
 }
 
+// ---- the generic path: the app as written (:62-202) on the library's noise_iq / fbm, which fall
+// back to the arithmetic hash outside the memo table.  Cold code: runs only for a pixel whose fast
+// path met a lattice index outside the table (huge u_time * wind_dir, or the table switched off).
+SBX_FN float generic_density(_in(vec3) pos_in) {
+    const vec3 pos = pos_in * cld_noise_factor;
+    return sbx_density_of(fbm(pos * 2.03f, 2.64f, .5f, .5f));
+}
+SBX_FN vec4 generic_clouds(_in(ray_t) eye) {
+    const vec3 projection = eye.direction / eye.direction.y;
+    vec3 origin = eye.origin + projection * 150.0f;
+    origin += wind_dir * u_time * (1.0f / cld_noise_factor);
+    volume_sampler_t cloud = construct_volume(origin);
+    float t = 0.0f;
+    const float dt = cld_thick / float(cld_march_steps);
+    for (int i = 0; i < cld_march_steps; i++) {
+        cloud.pos = cloud.origin + t * projection;
+        t += dt;
+        const float density = generic_density(cloud.pos);
+        if (!(density < .005f)) {
+            const float T_i = exp(-density * sigma_scattering * dt);
+            cloud.transmittance *= T_i;
+            vec3 lp = cloud.pos;
+            float tr = 1.0f;
+            lp += sun_dir * dt;
+            for (int j = 0; j < illum_march_steps; j++) {
+                tr *= exp(-generic_density(lp) * sigma_scattering * dt);
+                lp += sun_dir * dt;
+            }
+            cloud.radiance += (density * sigma_scattering) * (tr * sun_power * sbx_phase) * cloud.transmittance * dt;
+            cloud.alpha += (1.0f - T_i) * (1.0f - cloud.alpha);
+        }
+        if (cloud.alpha > .999f) break;
+    }
+    const float cutoff = dot(eye.direction, vec3(0.0f, 1.0f, 0.0f));
+    return vec4(cloud.radiance, cloud.alpha * smoothstep(.0f, .2f, cutoff));
+}
+// out of line, on a FRESH app object, so that the hot path's state never has its address taken
+static __device__ __noinline__ float4 sbx_generic_pixel(const sbx_launch* L, float ox, float oy, float oz, float dx,
+                                                        float dy, float dz) {
+    sbx_app a(L);
+    a.sbx_cov = 1.0f - a.cld_coverage;
+    ray_t eye;
+    eye.origin = vec3(ox, oy, oz);
+    eye.direction = vec3(dx, dy, dz);
+    a.sbx_phase = a.henyey_greenstein_phase_func(clamp(dot(a.sun_dir, eye.direction), 0.0f, 1.0f));
+    const vec4 c = a.generic_clouds(eye);
+    return make_float4(c.x, c.y, c.z, c.w);
+}
+
 SBX_FN vec3 render(_in(ray_t) eye_ray, _in(vec3) point_cam) {   // :204-218
     const vec3 sky = render_sky_color(eye_ray.direction);
     if (dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f) return sky;
-    const vec4 cld = render_clouds(eye_ray);
+    sbx_kmax = 0u;
+    vec4 cld = render_clouds(eye_ray);
+    if (sbx_kmax >= (unsigned)sbx_L->hash_span) {                       // table miss: redo the pixel
+        const float4 g = sbx_generic_pixel(sbx_L, eye_ray.origin.x, eye_ray.origin.y, eye_ray.origin.z,
+                                           eye_ray.direction.x, eye_ray.direction.y, eye_ray.direction.z);
+        cld = vec4(g.x, g.y, g.z, g.w);
+    }
     const vec3 col = mix(sky, cld.rgb, cld.a);
     return abs(col);
 }

@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,6 +58,7 @@ struct driver_api {
     CUresult (*EventElapsedTime)(float*, CUevent, CUevent);
     CUresult (*EventDestroy)(CUevent);
     CUresult (*GetErrorString)(CUresult, const char**);
+    CUresult (*PointerGetAttribute)(void*, CUpointer_attribute, CUdeviceptr);
 };
 
 std::mutex g_mutex;
@@ -102,6 +104,7 @@ driver_api* load_driver(std::string* err) {
     SBX_SYM(EventElapsedTime, "cuEventElapsedTime")
     SBX_SYM(EventDestroy, "cuEventDestroy_v2")
     SBX_SYM(GetErrorString, "cuGetErrorString")
+    SBX_SYM(PointerGetAttribute, "cuPointerGetAttribute")
 #undef SBX_SYM
     api.lib = lib;
     return &api;
@@ -147,6 +150,7 @@ struct sbx_ctx {
     int hash_lo = 0, hash_len = 0;
     int opt_hash_log2 = 18;       // table covers [-2^(k-1), 2^(k-1))
     int opt_use_hash = 1;
+    int opt_zero_copy = 1;        // sbx_render_host: store straight into pinned+mapped host frames
 
     CUdeviceptr frame = 0;        // internal frame for sbx_render_host
     size_t frame_bytes = 0;
@@ -434,6 +438,7 @@ int sbx_set_option(sbx_ctx* ctx, const char* key, int value) {
         return SBX_OK;
     }
     if (!std::strcmp(key, "use_hash_table")) { ctx->opt_use_hash = value ? 1 : 0; return SBX_OK; }
+    if (!std::strcmp(key, "host_zero_copy")) { ctx->opt_zero_copy = value ? 1 : 0; return SBX_OK; }
     return SBX_ERR_INVALID;
 }
 
@@ -484,15 +489,33 @@ int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard,
     return SBX_OK;
 }
 
+// Device-visible alias of a host frame, if the caller's buffer is pinned and mapped (cudaHostAlloc /
+// cuMemHostAlloc / a pinned torch tensor): 0 otherwise.
+static CUdeviceptr mapped_host_alias(sbx_ctx* ctx, float* host) {
+    unsigned mem_type = 0;
+    if (ctx->cu->PointerGetAttribute(&mem_type, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)(uintptr_t)host) != CUDA_SUCCESS)
+        return 0;
+    if (mem_type != CU_MEMORYTYPE_HOST) return 0;
+    CUdeviceptr dptr = 0;
+    if (ctx->cu->PointerGetAttribute(&dptr, CU_POINTER_ATTRIBUTE_DEVICE_POINTER, (CUdeviceptr)(uintptr_t)host) != CUDA_SUCCESS)
+        return 0;
+    return dptr;
+}
+
 int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* host_rgba) {
     if (!ctx || !p || !host_rgba || p->width <= 0 || p->height <= 0) return SBX_ERR_INVALID;
     sbx_shard s;
     if (!valid_shard(shard, &s)) return ctx->fail(SBX_ERR_INVALID, "bad shard");
     const size_t bytes = (size_t)shard_rows(s, p->height) * (size_t)p->width * 4 * sizeof(float);
     if (bytes == 0) return SBX_OK;
+    CUdeviceptr alias = 0;
     {
         ctx_scope scope(ctx);
-        if (bytes > ctx->frame_bytes) {
+        // Pinned + mapped destination: the kernel's float4 stores go straight over PCIe into the
+        // caller's frame while other pixels are still marching (the frame is write-only and each warp
+        // writes whole 128-byte lines), so there is no separate device->host copy to wait for.
+        if (ctx->opt_zero_copy && ((uintptr_t)host_rgba & 15u) == 0) alias = mapped_host_alias(ctx, host_rgba);
+        if (!alias && bytes > ctx->frame_bytes) {
             if (ctx->frame) ctx->cu->MemFree(ctx->frame);
             ctx->frame = 0;
             ctx->frame_bytes = 0;
@@ -500,14 +523,15 @@ int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, f
             ctx->frame_bytes = bytes;
         }
     }
-    int st = sbx_render_device(ctx, p, &s, (float*)ctx->frame, nullptr);
+    int st = sbx_render_device(ctx, p, &s, (float*)(alias ? alias : ctx->frame), nullptr);
     if (st != SBX_OK) return st;
     ctx_scope scope(ctx);
-    SBX_TRY(ctx->cu->MemcpyDtoHAsync(host_rgba, ctx->frame, bytes, nullptr), "cuMemcpyDtoHAsync");
+    if (!alias) SBX_TRY(ctx->cu->MemcpyDtoHAsync(host_rgba, ctx->frame, bytes, nullptr), "cuMemcpyDtoHAsync");
     SBX_TRY(ctx->cu->EventRecord(ctx->ev2, nullptr), "cuEventRecord");
     SBX_TRY(ctx->cu->StreamSynchronize(nullptr), "cuStreamSynchronize");
     float ms = 0.0f;
     if (ctx->cu->EventElapsedTime(&ms, ctx->ev1, ctx->ev2) == CUDA_SUCCESS) ctx->timing.d2h_ms = ms;
+    ctx->timing.zero_copy = alias ? 1 : 0;
     return SBX_OK;
 }
 

@@ -102,9 +102,19 @@ def test_native_clouds_kernel_matches_oracle_over_the_uniform_space(ov, renderer
     check(renderers("APP_CLOUDS", "plugin").render(w, h, u_time=t, **ov), want)
 
 
-def test_hash_memo_table_is_bit_identical_to_arithmetic(renderers):
+@pytest.mark.parametrize("t", [40.0, 700.0, 5000.0, 123456.0])
+def test_native_clouds_far_from_the_origin(t, renderers):
+    """wind_dir * u_time * 1000 moves the lattice indices out of the memo table: the hand-written kernel
+    must notice and redo those pixels on the generic (arithmetic-hash) path."""
+    w, h = 96, 54
+    want = loader.oracle_render("APP_CLOUDS", abi.default_params(w, h, t))
+    check(renderers("APP_CLOUDS", "native").render(w, h, u_time=t), want)
+
+
+@pytest.mark.parametrize("variant", ["plugin", "native"])
+def test_hash_memo_table_is_bit_identical_to_arithmetic(variant, renderers):
     """noise_iq.h memoises hash(n) for integer n; rendering with and without the table must agree."""
-    r = renderers("APP_CLOUDS", "plugin")
+    r = renderers("APP_CLOUDS", variant)
     a = r.render(160, 90, u_time=1.5)
     r.set_option("use_hash_table", 0)
     try:
@@ -155,6 +165,34 @@ def test_device_render_and_unshard_kernel(renderers):
     torch.cuda.synchronize()
     assert bits_equal(frame.cpu().numpy(), full.cpu().numpy())
     assert bits_equal(full.cpu().numpy(), r.render(w, h, u_time=t))
+
+
+def test_host_frame_paths_agree(renderers):
+    """sbx_render_host into pageable memory (render in HBM + copy) and into a pinned, mapped frame
+    (kernel stores go straight to the host over PCIe) give the same bits."""
+    import torch
+
+    w, h, t = 640, 360, 1.5
+    r = renderers("APP_CLOUDS", None)
+    p = abi.default_params(w, h, t)
+    pageable = r.render(w, h, u_time=t)
+    assert r.timing()["zero_copy"] == 0
+    pinned = torch.full((h, w, 4), float("nan"), dtype=torch.float32).pin_memory()
+    r.render_host_ptr(p, pinned.data_ptr())
+    assert r.timing()["zero_copy"] == 1
+    assert bits_equal(pinned.numpy(), pageable)
+    r.set_option("host_zero_copy", 0)
+    try:
+        pinned.fill_(float("nan"))
+        r.render_host_ptr(p, pinned.data_ptr())
+        assert r.timing()["zero_copy"] == 0
+        assert bits_equal(pinned.numpy(), pageable)
+    finally:
+        r.set_option("host_zero_copy", 1)
+    # sharded into a pinned part
+    part = torch.empty((len(abi.shard_rows(4, 3, 1, h)), w, 4), dtype=torch.float32).pin_memory()
+    r.render_host_ptr(p, part.data_ptr(), shard=(4, 3, 1))
+    assert bits_equal(part.numpy(), pageable[abi.shard_rows(4, 3, 1, h)])
 
 
 def test_deterministic_run_to_run(renderers):
