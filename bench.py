@@ -222,13 +222,17 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
     part = torch.empty((rows, w, 4), dtype=torch.float32, device=dev)
     frame = torch.empty((h, w, 4), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    fused = world > 1 and args.gather == "p2p"
+    shared = multi.SharedFrame(r, w, h) if fused else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    launches_per_step = 1 + ((world if rank == 0 else 0) if world > 1 else 0)
+    launches_per_step = 1 if (world == 1 or fused) else 1 + (world if rank == 0 else 0)
 
     def step():
         """kernel (+ gather + unshard at N > 1), all on `stream`"""
         if world == 1:
             r.render_into(p, part.data_ptr(), shard=shard, stream=stream.cuda_stream)
+        elif fused:
+            shared.render(p, stripe)
         else:
             multi.render_distributed(r, p, stripe, frame_out=frame, part_out=part)
 
@@ -257,6 +261,10 @@ def run_ours(args):
         if world == 1:
             step()
             ev[k][1].record(stream)
+        elif fused:
+            r.render_frame(p, shared.ptr, shard=shard, stream=stream.cuda_stream)
+            ev[k][1].record(stream)
+            dist.all_reduce(shared._done)      # stream-ordered "every rank's stripes have landed in rank 0's frame"
         else:
             r.render_into(p, part.data_ptr(), shard=shard, stream=stream.cuda_stream)
             ev[k][1].record(stream)
@@ -281,23 +289,42 @@ def run_ours(args):
     total_ms, total_kernel_ms = float(tot[0]), float(tot[1])
 
     # ---- e2e: the reference-facing host call, host buffers, copies inside the timed region --------
-    host = torch.empty((rows, w, 4), dtype=torch.float32).pin_memory()
     if args.no_zero_copy:
         r.set_option("host_zero_copy", 0)
+    if world == 1:
+        host = torch.empty((rows, w, 4), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            r.render_host_ptr(p, host.data_ptr(), shard=shard)        # sbx_render_host: synchronous
+        d2h_bytes = int(16 * rows * w)
+    else:
+        # N ranks: the frame is assembled on rank 0 (fused P2P stores or NCCL gather), then read back to the host there
+        host = torch.empty((h, w, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+
+        def e2e_step():
+            if fused:
+                shared.render(p, stripe)
+                src = shared.tensor() if rank == 0 else None
+            else:
+                src = multi.render_distributed(r, p, stripe, frame_out=frame, part_out=part)
+            if rank == 0:
+                host.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        d2h_bytes = int(16 * h * w)
     for _ in range(2):
-        r.render_host_ptr(p, host.data_ptr(), shard=shard)
+        e2e_step()
     barrier()
     e0 = time.perf_counter()
     for _ in range(args.steps):
-        r.render_host_ptr(p, host.data_ptr(), shard=shard)
-    torch.cuda.synchronize(dev)
+        e2e_step()
+    barrier()
     e_local = time.perf_counter() - e0
     e_t = torch.tensor([e_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e_t[0])
-    checksum = float(host[::97, ::89, :3].double().sum())   # device->host result actually read
-    zero_copy = bool(r.timing()["zero_copy"])
+    checksum = float(host[::97, ::89, :3].double().sum()) if host is not None else 0.0   # the host result is actually read
+    zero_copy = bool(r.timing()["zero_copy"]) if world == 1 else False
 
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_src = peaks()
@@ -316,17 +343,22 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s %dx%d u_time=%g %s" % (app, w, h, t, json.dumps(ov)), "variant": tm_variant(r, args),
                        "l2": "flushed between steps (256 MiB memset on the same stream, outside the timed events); the frame is write-only",
-                       "sharding": "none" if world == 1 else "%d-row stripes round-robin over %d ranks, gather to rank 0 + unshard inside the step" % (stripe, world),
+                       "sharding": "none" if world == 1 else (
+                           "%d-row stripes round-robin over %d ranks; every rank's render kernel stores its rows into rank 0's frame over NVLink "
+                           "(CUDA-IPC peer mapping), then a 1-element all-reduce as the completion barrier, all inside the step" % (stripe, world)
+                           if fused else
+                           "%d-row stripes round-robin over %d ranks, NCCL gather to rank 0 + unshard kernels inside the step" % (stripe, world)),
                        "grid": tm["grid_blocks"], "block": tm["block_threads"], "regs": tm["regs_per_thread"], "ctas_per_sm": tm["blocks_per_sm"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "sbx_render", "kernel_ms": avg_kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "write-only path: 16 B/pixel out, 0 in; the binding roof is FP32 issue (see fp32_issue)"},
             "e2e": {"value": px * args.steps / e2e_s * 1e-6, "unit": "Mpixels/s", "h2d_bytes_per_step": sbx_params_bytes(),
-                    "d2h_bytes_per_step": int(16 * rows * w), "checksum": checksum,
-                    "api": "sbx_render_host (C ABI) via shaderbox_b200.Renderer.render_host_ptr, pinned host frame",
+                    "d2h_bytes_per_step": d2h_bytes, "checksum": checksum,
+                    "api": ("sbx_render_host (C ABI) via shaderbox_b200.Renderer.render_host_ptr, pinned host frame" if world == 1 else
+                            "sbx_render_frame on every rank into rank 0's frame + one device->host copy of the frame on rank 0"),
                     "d2h": "kernel stores straight into the pinned+mapped host frame (zero-copy over PCIe)" if zero_copy
-                           else "frame rendered in HBM, then cuMemcpyDtoHAsync"},
+                           else "frame assembled in HBM, then one async copy to pinned host memory"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
@@ -337,6 +369,8 @@ def run_ours(args):
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["fp32_issue"] = fp32_issue(args.workload, avg_kernel_ms, sm_max_mhz, clocks)
         print(json.dumps(line), flush=True)
+    if shared is not None:
+        shared.close()
     r.close()
     if world > 1:
         dist.barrier()
@@ -388,6 +422,8 @@ def main():
     ap.add_argument("--workload", default="clouds1080", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default=None, help="native | plugin (default: native if present)")
     ap.add_argument("--stripe-rows", type=int, default=4)
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: p2p = render kernels store into rank 0's frame over NVLink; nccl = compacted parts + ncclGather + unshard")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: render in HBM and copy instead of storing into the host frame")

@@ -23,6 +23,10 @@
 #ifndef SBX_H_
 #define SBX_H_
 
+#if !defined(__CUDACC_RTC__)
+#include <stddef.h>   /* size_t */
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -119,6 +123,25 @@ int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_
  * frame is rendered in HBM and copied. */
 int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
                     float* host_rgba);
+
+/* Render the rows of `shard` straight into a FULL frame (height*width float4) at their frame rows --
+ * no compaction, no gather, no unshard.  dev_frame may live on ANOTHER GPU of the box (a pointer
+ * obtained from sbx_frame_import): the kernel's float4 stores then travel over NVLink while the
+ * remaining pixels are still being computed, which fuses the multi-GPU "gather" into the render
+ * kernel.  The caller orders completion across GPUs (e.g. a barrier after the launches). */
+int sbx_render_frame(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
+                     float* dev_frame, void* stream);
+
+/* Frame buffers that can be shared between the per-GPU processes of one box (CUDA IPC):
+ * alloc on the owner, export a 64-byte handle, import it in a peer process (enables peer access). */
+#define SBX_IPC_HANDLE_BYTES 64
+int sbx_frame_alloc(sbx_ctx* ctx, size_t bytes, float** dev_out);
+int sbx_frame_free(sbx_ctx* ctx, float* dev);
+int sbx_frame_export(sbx_ctx* ctx, const float* dev, unsigned char handle[SBX_IPC_HANDLE_BYTES]);
+int sbx_frame_import(sbx_ctx* ctx, const unsigned char handle[SBX_IPC_HANDLE_BYTES], float** dev_out);
+int sbx_frame_release(sbx_ctx* ctx, float* imported);
+/* Synchronous device->host read of a frame buffer (after ordering `stream`). */
+int sbx_frame_read(sbx_ctx* ctx, const float* dev, float* host, size_t bytes, void* stream);
 
 /* Scatter a compacted shard (as produced above / received from a peer) into a full frame on the
  * device: the de-interleave step after the multi-GPU gather. */

@@ -59,6 +59,9 @@ struct driver_api {
     CUresult (*EventDestroy)(CUevent);
     CUresult (*GetErrorString)(CUresult, const char**);
     CUresult (*PointerGetAttribute)(void*, CUpointer_attribute, CUdeviceptr);
+    CUresult (*IpcGetMemHandle)(CUipcMemHandle*, CUdeviceptr);
+    CUresult (*IpcOpenMemHandle)(CUdeviceptr*, CUipcMemHandle, unsigned);
+    CUresult (*IpcCloseMemHandle)(CUdeviceptr);
 };
 
 std::mutex g_mutex;
@@ -105,6 +108,9 @@ driver_api* load_driver(std::string* err) {
     SBX_SYM(EventDestroy, "cuEventDestroy_v2")
     SBX_SYM(GetErrorString, "cuGetErrorString")
     SBX_SYM(PointerGetAttribute, "cuPointerGetAttribute")
+    SBX_SYM(IpcGetMemHandle, "cuIpcGetMemHandle")
+    SBX_SYM(IpcOpenMemHandle, "cuIpcOpenMemHandle_v2")
+    SBX_SYM(IpcCloseMemHandle, "cuIpcCloseMemHandle")
 #undef SBX_SYM
     api.lib = lib;
     return &api;
@@ -442,7 +448,8 @@ int sbx_set_option(sbx_ctx* ctx, const char* key, int value) {
     return SBX_ERR_INVALID;
 }
 
-int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_rgba, void* stream_) {
+static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_rgba, void* stream_,
+                         int out_is_frame) {
     if (!ctx || !p || !dev_rgba || p->width <= 0 || p->height <= 0) return SBX_ERR_INVALID;
     if (!ctx->current) return ctx->fail(SBX_ERR_UNKNOWN_APP, "sbx_load_app was not called");
     sbx_shard s;
@@ -464,6 +471,7 @@ int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard,
     L.tiles_x = (p->width + SBX_TILE_W - 1) / SBX_TILE_W;
     L.tiles_y = (L.local_rows + SBX_TILE_H - 1) / SBX_TILE_H;
     L.out = dev_rgba;
+    L.out_is_frame = out_is_frame;
     L.hash_tab = (const float4*)ctx->hash_tab;
     L.hash_bias = SBX_HASH_MAGIC_BITS + ctx->hash_lo;
     L.hash_len = ctx->hash_len;
@@ -500,6 +508,66 @@ static CUdeviceptr mapped_host_alias(sbx_ctx* ctx, float* host) {
     if (ctx->cu->PointerGetAttribute(&dptr, CU_POINTER_ATTRIBUTE_DEVICE_POINTER, (CUdeviceptr)(uintptr_t)host) != CUDA_SUCCESS)
         return 0;
     return dptr;
+}
+
+int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_rgba, void* stream) {
+    return render_launch(ctx, p, shard, dev_rgba, stream, 0);
+}
+
+int sbx_render_frame(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_frame, void* stream) {
+    return render_launch(ctx, p, shard, dev_frame, stream, 1);
+}
+
+int sbx_frame_alloc(sbx_ctx* ctx, size_t bytes, float** out) {
+    if (!ctx || !out || bytes == 0) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    CUdeviceptr d = 0;
+    if (ctx->cu->MemAlloc(&d, bytes) != CUDA_SUCCESS) return ctx->fail(SBX_ERR_NOMEM, "cuMemAlloc(%zu) failed", bytes);
+    *out = (float*)(uintptr_t)d;
+    return SBX_OK;
+}
+
+int sbx_frame_free(sbx_ctx* ctx, float* dev) {
+    if (!ctx || !dev) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    SBX_TRY(ctx->cu->MemFree((CUdeviceptr)(uintptr_t)dev), "cuMemFree");
+    return SBX_OK;
+}
+
+int sbx_frame_export(sbx_ctx* ctx, const float* dev, unsigned char handle[SBX_IPC_HANDLE_BYTES]) {
+    if (!ctx || !dev || !handle) return SBX_ERR_INVALID;
+    static_assert(sizeof(CUipcMemHandle) == SBX_IPC_HANDLE_BYTES, "CUipcMemHandle is 64 bytes");
+    ctx_scope scope(ctx);
+    CUipcMemHandle h;
+    SBX_TRY(ctx->cu->IpcGetMemHandle(&h, (CUdeviceptr)(uintptr_t)dev), "cuIpcGetMemHandle");
+    std::memcpy(handle, &h, sizeof h);
+    return SBX_OK;
+}
+
+int sbx_frame_import(sbx_ctx* ctx, const unsigned char handle[SBX_IPC_HANDLE_BYTES], float** out) {
+    if (!ctx || !handle || !out) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    CUipcMemHandle h;
+    std::memcpy(&h, handle, sizeof h);
+    CUdeviceptr d = 0;
+    SBX_TRY(ctx->cu->IpcOpenMemHandle(&d, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS), "cuIpcOpenMemHandle");
+    *out = (float*)(uintptr_t)d;
+    return SBX_OK;
+}
+
+int sbx_frame_release(sbx_ctx* ctx, float* imported) {
+    if (!ctx || !imported) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    SBX_TRY(ctx->cu->IpcCloseMemHandle((CUdeviceptr)(uintptr_t)imported), "cuIpcCloseMemHandle");
+    return SBX_OK;
+}
+
+int sbx_frame_read(sbx_ctx* ctx, const float* dev, float* host, size_t bytes, void* stream) {
+    if (!ctx || !dev || !host) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    SBX_TRY(ctx->cu->MemcpyDtoHAsync(host, (CUdeviceptr)(uintptr_t)dev, bytes, (CUstream)stream), "cuMemcpyDtoHAsync");
+    SBX_TRY(ctx->cu->StreamSynchronize((CUstream)stream), "cuStreamSynchronize");
+    return SBX_OK;
 }
 
 int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* host_rgba) {

@@ -49,6 +49,13 @@ def lib():
         L.sbx_shard_rows.argtypes = [P(Shard), C.c_int]
         L.sbx_render_device.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_void_p]
         L.sbx_render_host.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p]
+        L.sbx_render_frame.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_void_p]
+        L.sbx_frame_alloc.argtypes = [C.c_void_p, C.c_size_t, P(C.c_void_p)]
+        L.sbx_frame_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.sbx_frame_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+        L.sbx_frame_import.argtypes = [C.c_void_p, C.c_char_p, P(C.c_void_p)]
+        L.sbx_frame_release.argtypes = [C.c_void_p, C.c_void_p]
+        L.sbx_frame_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.sbx_unshard_device.argtypes = [C.c_void_p, C.c_int, C.c_int, P(Shard), C.c_void_p, C.c_void_p, C.c_void_p]
         L.sbx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.sbx_last_timing.argtypes = [C.c_void_p, P(Timing)]
@@ -60,7 +67,8 @@ def lib():
 EXPORTS = (
     "sbx_default_params", "sbx_create", "sbx_destroy", "sbx_load_app", "sbx_compile_app", "sbx_shard_rows",
     "sbx_render_device", "sbx_render_host", "sbx_unshard_device", "sbx_set_option", "sbx_last_timing",
-    "sbx_last_error", "sbx_strerror", "sbx_version", "sbx_eval_op",
+    "sbx_last_error", "sbx_strerror", "sbx_version", "sbx_eval_op", "sbx_render_frame", "sbx_frame_alloc",
+    "sbx_frame_free", "sbx_frame_export", "sbx_frame_import", "sbx_frame_release", "sbx_frame_read",
 )
 
 
@@ -129,6 +137,39 @@ class Renderer:
         sh = Shard(*shard) if shard is not None else Shard(1, 1, 0)
         self._check(self._L.sbx_render_device(self._ctx, C.byref(params), C.byref(sh), C.c_void_p(dev_ptr),
                                               C.c_void_p(stream)), "sbx_render_device")
+
+    def render_frame(self, params, dev_frame_ptr, shard=None, stream=0):
+        """Render this shard's rows straight into a FULL frame at `dev_frame_ptr` (may be a peer GPU's)."""
+        sh = Shard(*shard) if shard is not None else Shard(1, 1, 0)
+        self._check(self._L.sbx_render_frame(self._ctx, C.byref(params), C.byref(sh), C.c_void_p(dev_frame_ptr),
+                                             C.c_void_p(stream)), "sbx_render_frame")
+
+    def frame_alloc(self, nbytes):
+        out = C.c_void_p()
+        self._check(self._L.sbx_frame_alloc(self._ctx, nbytes, C.byref(out)), "sbx_frame_alloc")
+        return out.value
+
+    def frame_free(self, ptr):
+        self._check(self._L.sbx_frame_free(self._ctx, C.c_void_p(ptr)), "sbx_frame_free")
+
+    def frame_export(self, ptr):
+        buf = C.create_string_buffer(64)
+        self._check(self._L.sbx_frame_export(self._ctx, C.c_void_p(ptr), buf), "sbx_frame_export")
+        return buf.raw
+
+    def frame_import(self, handle):
+        out = C.c_void_p()
+        self._check(self._L.sbx_frame_import(self._ctx, handle, C.byref(out)), "sbx_frame_import")
+        return out.value
+
+    def frame_release(self, ptr):
+        self._check(self._L.sbx_frame_release(self._ctx, C.c_void_p(ptr)), "sbx_frame_release")
+
+    def frame_read(self, ptr, height, width, stream=0):
+        out = np.empty((height, width, 4), dtype=np.float32)
+        self._check(self._L.sbx_frame_read(self._ctx, C.c_void_p(ptr), out.ctypes.data_as(C.c_void_p), out.nbytes,
+                                           C.c_void_p(stream)), "sbx_frame_read")
+        return out
 
     def render_host_ptr(self, params, host_ptr, shard=None):
         """Render + copy to a host buffer given by address (e.g. a pinned torch tensor)."""

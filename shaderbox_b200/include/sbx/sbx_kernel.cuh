@@ -106,7 +106,7 @@ sbx_render(const __grid_constant__ sbx_launch L) {
     sbx_glsl::vec4 c;
     app.mainImage(c, sbx_glsl::vec2(float(x) + 0.5f, float(y) + 0.5f));
 
-    float4* dst = reinterpret_cast<float4*>(L.out) + (size_t)lr * (size_t)L.p.width + (size_t)x;
+    float4* dst = reinterpret_cast<float4*>(L.out) + (size_t)(L.out_is_frame ? y : lr) * (size_t)L.p.width + (size_t)x;
     __stcs(dst, make_float4(c.x, c.y, c.z, c.w));
 }
 

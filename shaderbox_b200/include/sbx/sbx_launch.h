@@ -23,7 +23,8 @@ typedef struct sbx_launch {
     int hash_bias;              /* SBX_HASH_MAGIC_BITS + hash_lo */
     int hash_len;
     int hash_span;              /* hash_len - 113: base indices k whose second z-slice k+113 is tabulated too */
-    int pad0;
+    int out_is_frame;           /* 0: out rows are this launch's local (compacted) rows; 1: out is the FULL frame
+                                   (possibly a peer GPU's, mapped over NVLink) and rows land at their frame row */
     const void* lut;            /* SBX_LUT_MATH_BYTES of exp2/log2 tables in global memory (sbx_math.h) */
 } sbx_launch;
 

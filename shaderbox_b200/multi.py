@@ -86,3 +86,59 @@ def render_distributed(renderer, params, stripe_rows=DEFAULT_STRIPE_ROWS, group=
         if part.shape[0]:
             renderer.unshard(w, h, shard_of(r, world, stripe_rows), part.data_ptr(), frame_out.data_ptr(), stream=stream)
     return frame_out
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ holder so a frame pointer owned by libsbx can be viewed as a torch tensor."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class SharedFrame:
+    """The full frame on rank `dst`, mapped into every rank's address space with CUDA IPC
+    (sbx_frame_alloc / sbx_frame_export / sbx_frame_import), so each rank's render kernel stores its
+    stripes straight into it over NVLink: the gather is fused into the render kernel."""
+
+    def __init__(self, renderer, width, height, dst=0, group=None):
+        self.renderer, self.width, self.height, self.dst, self.group = renderer, int(width), int(height), dst, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.nbytes = self.width * self.height * 16
+        self.owner = self.rank == dst
+        handle = [None]
+        if self.owner:
+            self.ptr = renderer.frame_alloc(self.nbytes)
+            handle[0] = renderer.frame_export(self.ptr) if self.world > 1 else None
+        if self.world > 1:
+            dist.broadcast_object_list(handle, src=dst, group=group)
+            if not self.owner:
+                self.ptr = renderer.frame_import(handle[0])
+            dist.barrier(group)
+        dev = torch.device("cuda", renderer.device)
+        self._done = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def tensor(self):
+        """[height, width, 4] float32 view of the frame (owner rank only)."""
+        assert self.owner
+        return torch.as_tensor(_CudaArray(self.ptr, (self.height, self.width, 4)), device=torch.device("cuda", self.renderer.device))
+
+    def render(self, params, stripe_rows=DEFAULT_STRIPE_ROWS):
+        """One frame: every rank launches its stripes into the shared frame, then a one-element all-reduce
+        on the same stream orders "all stripes have landed" before anything rank `dst` enqueues next."""
+        assert params.width == self.width and params.height == self.height
+        dev = torch.device("cuda", self.renderer.device)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self.renderer.render_frame(params, self.ptr, shard=shard_of(self.rank, self.world, stripe_rows), stream=stream)
+        if self.world > 1:
+            dist.all_reduce(self._done, group=self.group)
+
+    def close(self):
+        if self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(self.group)
+        if self.owner:
+            self.renderer.frame_free(self.ptr)
+        else:
+            self.renderer.frame_release(self.ptr)
+        self.ptr = None
