@@ -42,6 +42,24 @@ __global__ void k_packed(float* out, float a, float b, int c) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+template <int NINT>
+__global__ void k_packed_ma(float* out, float a, float b, int c) {
+    float2 x[CH]; int y[8];
+    const float2 A = make_float2(a, a), B = make_float2(b, b);
+    for (int i = 0; i < CH; ++i) x[i] = make_float2(a + 2 * i + threadIdx.x, a + 2 * i + 1 + threadIdx.x);
+    for (int i = 0; i < 8; ++i) y[i] = c + i + threadIdx.x;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) { x[i] = __fmul2_rn(x[i], A); x[i] = __fadd2_rn(x[i], B); }   // 8 FMUL2 + 8 FADD2
+#pragma unroll
+        for (int i = 0; i < NINT; ++i) { y[i % 8] = (y[i % 8] ^ c) + (y[(i + 1) % 8] >> 3); }
+    }
+    float s = 0;
+    for (int i = 0; i < CH; ++i) s += x[i].x + x[i].y;
+    for (int i = 0; i < 8; ++i) s += y[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class F> float timeit(F f) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     f(); cudaDeviceSynchronize();
@@ -61,6 +79,7 @@ int main() {
     RUN("scalar 32 FMUL/FADD", k_scalar, 0) RUN("packed 16 FFMA2", k_packed, 0)
     RUN("scalar 32 FMUL/FADD", k_scalar, 8) RUN("packed 16 FFMA2", k_packed, 8)
     RUN("scalar 32 FMUL/FADD", k_scalar, 16) RUN("packed 16 FFMA2", k_packed, 16)
+    RUN("packed 8 FMUL2 + 8 FADD2", k_packed_ma, 0) RUN("packed 8 FMUL2 + 8 FADD2", k_packed_ma, 8) RUN("packed 8 FMUL2 + 8 FADD2", k_packed_ma, 16)
     printf("{\"sms\": %d, \"clock_khz\": %d}\n", sms, khz);
     return 0;
 }
