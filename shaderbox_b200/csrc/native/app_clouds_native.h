@@ -4,21 +4,31 @@
 // built by nvcc into images/APP_CLOUDS.native.cubin.  The frame is BIT-IDENTICAL to the unchanged
 // reference header compiled as a plugin (tests/test_gpu_parity.py compares both with the oracle):
 // every value that reaches the pixel is produced by the reference's operations in the reference's
-// order.  What is hand-tuned is which of those operations are executed at all (ncu, profiles/r01b:
-// the kernel is FP32-issue bound, 97 % of issued instructions are the fbm octaves):
+// order.  What is hand-tuned is which of those operations are executed at all, and how many issue
+// slots the remaining ones take (ncu, profiles/: the kernel is instruction-issue bound, ~90 % of
+// issued instructions are the fbm octaves of density_func):
 //
+//  * packed fp32 (FFMA2).  The octave arithmetic runs two lanes per instruction: x/y for the
+//    position chain and the smoothstep weights, the two z-slices of a noise cell for the x/y
+//    interpolation (the memo table stores z-neighbours adjacent, noise_iq.h), octave pairs in the
+//    light march.  Every lane performs exactly the scalar operation's single rounding
+//    (sbx_vec.cuh, pk_*).
 //  * lazy octaves in the view march (density_func :62-86).  density = shape * smoothstep(cov,
 //    cov + .0135, shape) is exactly +0 whenever shape <= cov, and the fbm octaves still to come can
 //    add at most their gains (noise_iq <= 1): after octave i, t_i + sum(remaining H) <= cov (minus a
 //    1e-5 guard, orders of magnitude above the few ulps the fp32 sums can gain) proves the result
 //    is 0 without evaluating them.  Half of the sky is empty (cld_coverage .535).
+//  * smoothstep without its division outside the 0.0135-wide band: with a = shape - cov and
+//    b = (cov + .0135) - cov > 0 (both as rounded by the reference), a <= 0 gives t = 0 and the
+//    density +0; a >= b gives a/b >= 1 (division is monotonic, 1 is representable), t = 1 and
+//    the density shape * (1*1*(3-2)) = shape.  Only samples inside the band divide.
 //  * z-slice reuse in the light march (illuminate_volume :107-113).  noise_iq interpolates x, then
 //    y, then z (src/noise_iq.h:19-23): the two bilinear z-slice values y0, y1 of an octave depend
 //    only on (p.x, p.y, floor(p.z)).  The light march steps by L*dt; when that leaves x and y
-//    bit-unchanged (the default sun_dir (0,0,-1) of src/uniform_buffer.h:42) and z stays in the
-//    same lattice cell, an octave is one floor, one smoothstep weight and one mix.  Equality is
-//    checked on the bits, per sample and per octave, so any sun direction stays exact; it just
-//    falls back to the full octave.
+//    bit-unchanged (the default sun_dir (0,0,-1) of src/uniform_buffer.h:42) an octave whose z
+//    stays in its lattice cell is one floor, one smoothstep weight and one mix; an octave that
+//    crossed into the next cell is re-sliced alone.  Equality is checked on the values, per sample
+//    and per octave, so any sun direction stays exact; it just re-slices every octave.
 //  * exp(-0 * sigma * dt) == 1 exactly: empty light-march samples skip the exponential (:110-113).
 //  * the Henyey-Greenstein factor of illuminate_volume (:121) depends only on the ray, not on the
 //    sample: one pow per ray instead of one per in-cloud step.
@@ -39,12 +49,12 @@ DECL_FBM_FUNC(fbm, 4, noise_iq(p))   // :59, the generic form: used when a latti
 
 float sbx_phase;       // henyey_greenstein_phase_func(clamp(dot(L, V), 0, 1)) of :121, per ray
 float sbx_cov;         // 1 - cld_coverage (:83)
-// z-slice memo of the last fully evaluated sample: position x/y it was taken at and, per octave,
-// the lattice z and the two bilinear slice values
+float sbx_band_lo, sbx_band_hi;   // smoothstep shortcuts: (shape - cov) <= lo -> 0, >= hi -> 1 (see sbx_density_of)
+// z-slice memo of the last sliced sample: position x/y it was taken at and, per octave, the
+// lattice z and the two bilinear slice values (y0, y1)
 float sbx_mx, sbx_my;
 float sbx_mz0, sbx_mz1, sbx_mz2, sbx_mz3;
-float sbx_a0, sbx_a1, sbx_a2, sbx_a3;   // y0 of octave 0..3
-float sbx_b0, sbx_b1, sbx_b2, sbx_b3;   // y1 of octave 0..3
+float2 sbx_ys0, sbx_ys1, sbx_ys2, sbx_ys3;
 unsigned sbx_kmax;     // largest table index this pixel asked for (see render)
 
 SBX_FN void setup_camera(_inout(vec3) eye, _inout(vec3) look_at) {   // :23-30
@@ -63,83 +73,127 @@ SBX_FN vec3 render_sky_color(_in(vec3) eye_dir) {   // :36-46
     return abs(sky);
 }
 
-SBX_FN float sbx_weight(float f) { return f * f * __fmaf_rn(f, -2.0f, 3.0f); }   // f*f*(3 - 2f), noise_iq.h:16
-
-// one octave of noise_iq (src/noise_iq.h:11-23) evaluated in full; returns its two z-slices too.
-// The lattice index is clamped into the memo table and the largest one remembered: a pixel that
-// ever asked for an entry outside the table is recomputed on the generic path (render()).
-SBX_FN float octave_full(_in(vec3) x, float& mz, float& y0, float& y1) {
-    const vec3 p = floor(x);
-    const float wx = sbx_weight(x.x - p.x), wy = sbx_weight(x.y - p.y), wz = sbx_weight(x.z - p.z);
-    const float n = p.x + p.y * 157.0f + 113.0f * p.z;
+// The two z-slices (y0, y1) of one noise_iq octave (src/noise_iq.h:11-23) at lattice cell
+// (px, py, pz) with smoothed x/y weights.  The lattice index is clamped into the memo table and
+// the largest one remembered: a pixel that ever asked for an entry outside the table is
+// recomputed on the generic path (render()).
+SBX_FN float2 sbx_slices(float2 pxy, float pz, float2 wxy) {
+    const float n = pxy.x + pxy.y * 157.0f + 113.0f * pz;
     const unsigned k = (unsigned)(__float_as_int(n + 12582912.0f) - sbx_L->hash_bias);
     sbx_kmax = ::max(sbx_kmax, k);
-    const float4* __restrict__ e = sbx_L->hash_tab + ::min(k, (unsigned)sbx_L->hash_span - 1u);
-    const float4 z0 = __ldg(e), z1 = __ldg(e + 113);
-    y0 = mix(mix(z0.x, z0.y, wx), mix(z0.z, z0.w, wx), wy);
-    y1 = mix(mix(z1.x, z1.y, wx), mix(z1.z, z1.w, wx), wy);
-    mz = p.z;
-    return mix(y0, y1, wz);
+    const float4* __restrict__ e = sbx_L->hash_tab + 2u * ::min(k, (unsigned)sbx_L->hash_span - 1u);
+    const float4 lo = __ldg(e), hi = __ldg(e + 1);
+    const float2 axy = pk_one_minus(wxy);
+    return pk_mix(pk_mix(pk(lo.x, lo.y), pk(lo.z, lo.w), axy.x, wxy.x),
+                  pk_mix(pk(hi.x, hi.y), pk(hi.z, hi.w), axy.x, wxy.x), axy.y, wxy.y);
 }
 
-SBX_FN float sbx_density_of(float shape) { return shape * smoothstep(sbx_cov, sbx_cov + .0135f, shape); }   // :83-84
+// one octave at p = (pxy, pz), evaluated in full; leaves its lattice z and slices in the memo
+SBX_FN float sbx_octave(float2 pxy, float pz, float& mz, float2& ys) {
+    const float2 cxy = pk(floor(pxy.x), floor(pxy.y));
+    const float cz = floor(pz);
+    ys = sbx_slices(cxy, cz, sbx_noise_weight(pk_sub(pxy, cxy)));
+    mz = cz;
+    return sbx_noise_zmix(ys, sbx_noise_weight(pz - cz));
+}
+
+// shape * smoothstep(cov, cov + .0135, shape)   (:83-84), dividing only inside the band
+SBX_FN float sbx_density_of(float shape) {
+    const float a = shape - sbx_cov;
+    if (a <= sbx_band_lo) return 0.0f;
+    if (a >= sbx_band_hi) return shape;
+    return shape * smoothstep(sbx_cov, sbx_cov + .0135f, shape);
+}
 
 // density_func (:62-86) for a view-march sample: fbm(pos * 2.03, 2.64, .5, .5) of src/fbm.h:6
 // unrolled (H = .5 .25 .125 .0625) with the lazy-octave exits
-SBX_FN float density_view(_in(vec3) pos_in) {
-    const vec3 pos = pos_in * cld_noise_factor;
-    vec3 p = pos * 2.03f;
+SBX_FN float density_view(float2 pos_xy, float pos_z) {
+    float2 pxy = pk_mul(pk_mul(pos_xy, cld_noise_factor), 2.03f);     // pos = pos_in * .001; p = pos * 2.03
+    float pz = pos_z * cld_noise_factor * 2.03f;
     const float guard = 1e-5f;
-    sbx_mx = pos_in.x; sbx_my = pos_in.y;
-    float t = octave_full(p, sbx_mz0, sbx_a0, sbx_b0) * .5f;      // 0 + n*.5 == n*.5 (n >= +0)
+    sbx_mx = pos_xy.x; sbx_my = pos_xy.y;
+    float t = sbx_octave(pxy, pz, sbx_mz0, sbx_ys0) * .5f;            // 0 + n*.5 == n*.5 (n >= +0)
     if (t <= sbx_cov - .4375f - guard) return 0.0f;
-    p *= 2.64f;
-    t += octave_full(p, sbx_mz1, sbx_a1, sbx_b1) * .25f;
+    pxy = pk_mul(pxy, 2.64f); pz *= 2.64f;
+    t += sbx_octave(pxy, pz, sbx_mz1, sbx_ys1) * .25f;
     if (t <= sbx_cov - .1875f - guard) return 0.0f;
-    p *= 2.64f;
-    t += octave_full(p, sbx_mz2, sbx_a2, sbx_b2) * .125f;
+    pxy = pk_mul(pxy, 2.64f); pz *= 2.64f;
+    t += sbx_octave(pxy, pz, sbx_mz2, sbx_ys2) * .125f;
     if (t <= sbx_cov - .0625f - guard) return 0.0f;
-    p *= 2.64f;
-    t += octave_full(p, sbx_mz3, sbx_a3, sbx_b3) * .0625f;
+    pxy = pk_mul(pxy, 2.64f); pz *= 2.64f;
+    t += sbx_octave(pxy, pz, sbx_mz3, sbx_ys3) * .0625f;
     return sbx_density_of(t);
 }
 
-// density_func for a light-march sample.  If x and y are bit-identical to the memoised sample and
-// every octave stays in its lattice cell along z, each octave is one weight and one mix.
-SBX_FN float density_light(_in(vec3) pos_in) {
-    const float z0 = pos_in.z * cld_noise_factor * 2.03f;         // the z chain of p = pos*.001*2.03, p *= 2.64
-    const float z1 = z0 * 2.64f, z2 = z1 * 2.64f, z3 = z2 * 2.64f;
-    const float c0 = floor(z0), c1 = floor(z1), c2 = floor(z2), c3 = floor(z3);
-    float t;
-    if (pos_in.x == sbx_mx && pos_in.y == sbx_my && c0 == sbx_mz0 && c1 == sbx_mz1 && c2 == sbx_mz2 && c3 == sbx_mz3) {
-        t = mix(sbx_a0, sbx_b0, sbx_weight(z0 - c0)) * .5f;
-        t += mix(sbx_a1, sbx_b1, sbx_weight(z1 - c1)) * .25f;
-        t += mix(sbx_a2, sbx_b2, sbx_weight(z2 - c2)) * .125f;
-        t += mix(sbx_a3, sbx_b3, sbx_weight(z3 - c3)) * .0625f;
-    } else {
-        const vec3 pos = pos_in * cld_noise_factor;
-        vec3 p = pos * 2.03f;
-        sbx_mx = pos_in.x; sbx_my = pos_in.y;
-        t = octave_full(p, sbx_mz0, sbx_a0, sbx_b0) * .5f;
-        p *= 2.64f;
-        t += octave_full(p, sbx_mz1, sbx_a1, sbx_b1) * .25f;
-        p *= 2.64f;
-        t += octave_full(p, sbx_mz2, sbx_a2, sbx_b2) * .125f;
-        p *= 2.64f;
-        t += octave_full(p, sbx_mz3, sbx_a3, sbx_b3) * .0625f;
-    }
-    return sbx_density_of(t);
-}
-
-SBX_FN float illuminate_volume(_in(vec3) origin, _in(vec3) L) {   // :91-123
+// illuminate_volume (:91-123).  `origin` is the view sample just evaluated by density_view, so
+// the memo holds its slices.  Per light sample: the z chain of the four octaves, their lattice
+// cells, and -- if x and y still equal the memo's -- only the octaves that left their cell are
+// re-sliced.  Then every octave is one weight and one mix of its two slices, two octaves per
+// instruction.
+SBX_FN float illuminate_volume(float2 origin_xy, float origin_z, _in(vec3) L) {
     const float dt = cld_thick / float(cld_march_steps);
-    vec3 pos = origin;
+    const vec3 step = L * dt;
+    float2 pos_xy = pk_add(origin_xy, pk(step.x, step.y));     // don't sample just where the main raymarcher is
+    float pos_z = origin_z + step.z;
     float transmittance = 1.0f;
-    pos += L * dt;   // don't sample just where the main raymarcher is
+    // slices transposed to octave pairs: (y0 of octave 0, y0 of octave 1), ...
+    float2 a01 = pk(sbx_ys0.x, sbx_ys1.x), b01 = pk(sbx_ys0.y, sbx_ys1.y);
+    float2 a23 = pk(sbx_ys2.x, sbx_ys3.x), b23 = pk(sbx_ys2.y, sbx_ys3.y);
+    float2 m01 = pk(sbx_mz0, sbx_mz1), m23 = pk(sbx_mz2, sbx_mz3);
     for (int i = 0; i < illum_march_steps; i++) {
-        const float density = density_light(pos);
+        const float z0 = pos_z * cld_noise_factor * 2.03f;     // the z chain of p = pos*.001*2.03, p *= 2.64
+        const float z1 = z0 * 2.64f, z2 = z1 * 2.64f, z3 = z2 * 2.64f;
+        const float2 z01 = pk(z0, z1), z23 = pk(z2, z3);
+        // fract(z) against the memoised lattice z: f = z - m lies in [0, 1) only if floor(z) == m (z < m gives
+        // f < 0, z >= m + 1 gives f >= 1: rounding is monotonic), and then it IS the reference's z - floor(z).
+        // As unsigned integers the floats of [+0, 1) are exactly the values below bits(1.0f).
+        float2 f01 = pk_sub(z01, m01), f23 = pk_sub(z23, m23);
+        const unsigned worst = ::max(::max(__float_as_uint(f01.x), __float_as_uint(f01.y)),
+                                     ::max(__float_as_uint(f23.x), __float_as_uint(f23.y)));
+        const bool same_xy = pos_xy.x == sbx_mx && pos_xy.y == sbx_my;
+        if (!(same_xy && worst < 0x3f800000u)) {
+            // re-slice the octaves that left their cell (all of them if x or y changed)
+            const float2 c01 = pk(floor(z0), floor(z1)), c23 = pk(floor(z2), floor(z3));
+            float2 pxy = pk_mul(pk_mul(pos_xy, cld_noise_factor), 2.03f);
+            float2 cxy;
+            if (!(same_xy && c01.x == m01.x)) {
+                cxy = pk(floor(pxy.x), floor(pxy.y));
+                const float2 ys = sbx_slices(cxy, c01.x, sbx_noise_weight(pk_sub(pxy, cxy)));
+                a01.x = ys.x; b01.x = ys.y; m01.x = c01.x;
+            }
+            pxy = pk_mul(pxy, 2.64f);
+            if (!(same_xy && c01.y == m01.y)) {
+                cxy = pk(floor(pxy.x), floor(pxy.y));
+                const float2 ys = sbx_slices(cxy, c01.y, sbx_noise_weight(pk_sub(pxy, cxy)));
+                a01.y = ys.x; b01.y = ys.y; m01.y = c01.y;
+            }
+            pxy = pk_mul(pxy, 2.64f);
+            if (!(same_xy && c23.x == m23.x)) {
+                cxy = pk(floor(pxy.x), floor(pxy.y));
+                const float2 ys = sbx_slices(cxy, c23.x, sbx_noise_weight(pk_sub(pxy, cxy)));
+                a23.x = ys.x; b23.x = ys.y; m23.x = c23.x;
+            }
+            pxy = pk_mul(pxy, 2.64f);
+            if (!(same_xy && c23.y == m23.y)) {
+                cxy = pk(floor(pxy.x), floor(pxy.y));
+                const float2 ys = sbx_slices(cxy, c23.y, sbx_noise_weight(pk_sub(pxy, cxy)));
+                a23.y = ys.x; b23.y = ys.y; m23.y = c23.y;
+            }
+            sbx_mx = pos_xy.x; sbx_my = pos_xy.y;
+            f01 = pk_sub(z01, m01); f23 = pk_sub(z23, m23);
+        }
+        const float2 w01 = sbx_noise_weight(f01), w23 = sbx_noise_weight(f23);
+        const float2 n01 = pk_mix(a01, b01, pk_one_minus(w01), w01);          // noise_iq of octaves 0, 1
+        const float2 n23 = pk_mix(a23, b23, pk_one_minus(w23), w23);          // octaves 2, 3
+        const float2 s01 = pk_mul(n01, pk(.5f, .25f)), s23 = pk_mul(n23, pk(.125f, .0625f));
+        const float density = sbx_density_of(((s01.x + s01.y) + s23.x) + s23.y);
+#ifdef SBX_X_NOEXP
+        if (density != 0.0f) transmittance *= (1.0f - density * sigma_scattering * dt);
+#else
         if (density != 0.0f) transmittance *= exp(-density * sigma_scattering * dt);   // exp(-0) == 1
-        pos += L * dt;
+#endif
+        pos_xy = pk_add(pos_xy, pk(step.x, step.y));
+        pos_z += step.z;
     }
     return transmittance * sun_power * sbx_phase;
 }
@@ -150,26 +204,34 @@ SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-202
     origin += wind_dir * u_time * (1.0f / cld_noise_factor);
 
     sbx_cov = 1.0f - cld_coverage;
+    const float band = (sbx_cov + .0135f) - sbx_cov;                      // e1 - e0 of the smoothstep (:84)
+    sbx_band_lo = band > 0.0f ? 0.0f : -__int_as_float(0x7f800000);        // a degenerate band never shortcuts
+    sbx_band_hi = band > 0.0f ? band : __int_as_float(0x7f800000);
     sbx_phase = henyey_greenstein_phase_func(clamp(dot(sun_dir, eye.direction), 0.0f, 1.0f));
 
-    volume_sampler_t cloud = construct_volume(origin);
-    float t = 0.0f;
+    const float2 origin_xy = pk(origin.x, origin.y), proj_xy = pk(projection.x, projection.y);
+    float transmittance = 1.0f, radiance = 0.0f, alpha = 0.0f;             // volume_sampler_t (volumetric.h:47-68);
+    float t = 0.0f;                                                        // radiance is one float: vec3 += float
     const float dt = cld_thick / float(cld_march_steps);
     for (int i = 0; i < cld_march_steps; i++) {
-        cloud.pos = cloud.origin + t * projection;
+        const float2 pos_xy = pk_add(origin_xy, pk_mul(proj_xy, t));       // cloud.pos = cloud.origin + t * projection
+        const float pos_z = origin.z + t * projection.z;
         t += dt;
-        const float density = density_view(cloud.pos);
+        const float density = density_view(pos_xy, pos_z);
         if (!(density < .005f)) {                                          // integrate_volume, :125-148
             const float T_i = exp(-density * sigma_scattering * dt);       // Beer-Lambert
-            cloud.transmittance *= T_i;
-            cloud.radiance += (density * sigma_scattering) * illuminate_volume(cloud.pos, sun_dir) *
-                              cloud.transmittance * dt;
-            cloud.alpha += (1.0f - T_i) * (1.0f - cloud.alpha);
+            transmittance *= T_i;
+#ifdef SBX_X_NOLIGHT
+            radiance += (density * sigma_scattering) * (sbx_ys0.x + sbx_ys1.y + sbx_ys2.x + sbx_ys3.y + sbx_mz0 + sbx_mz1 + sbx_mz2 + sbx_mz3) * transmittance * dt;
+#else
+            radiance += (density * sigma_scattering) * illuminate_volume(pos_xy, pos_z, sun_dir) * transmittance * dt;
+#endif
+            alpha += (1.0f - T_i) * (1.0f - alpha);
         }
-        if (cloud.alpha > .999f) break;
+        if (alpha > .999f) break;
     }
     const float cutoff = dot(eye.direction, vec3(0.0f, 1.0f, 0.0f));
-    return vec4(cloud.radiance, cloud.alpha * smoothstep(.0f, .2f, cutoff));
+    return vec4(radiance, radiance, radiance, alpha * smoothstep(.0f, .2f, cutoff));
 }
 
 // ---- the generic path: the app as written (:62-202) on the library's noise_iq / fbm, which fall
@@ -177,7 +239,8 @@ SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-202
 // path met a lattice index outside the table (huge u_time * wind_dir, or the table switched off).
 SBX_FN float generic_density(_in(vec3) pos_in) {
     const vec3 pos = pos_in * cld_noise_factor;
-    return sbx_density_of(fbm(pos * 2.03f, 2.64f, .5f, .5f));
+    const float shape = fbm(pos * 2.03f, 2.64f, .5f, .5f);
+    return shape * smoothstep(sbx_cov, sbx_cov + .0135f, shape);
 }
 SBX_FN vec4 generic_clouds(_in(ray_t) eye) {
     const vec3 projection = eye.direction / eye.direction.y;

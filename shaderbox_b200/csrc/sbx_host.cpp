@@ -152,7 +152,7 @@ struct sbx_ctx {
     CUfunction k_hash = nullptr, k_unshard = nullptr, k_eval = nullptr;
 
     CUdeviceptr lut = 0;          // SBX_LUT_MATH_BYTES
-    CUdeviceptr hash_tab = 0;     // float4 entries
+    CUdeviceptr hash_tab = 0;     // 2 float4 per entry (noise_iq.h)
     int hash_lo = 0, hash_len = 0;
     int opt_hash_log2 = 18;       // table covers [-2^(k-1), 2^(k-1))
     int opt_use_hash = 1;
@@ -224,7 +224,7 @@ int ensure_tables(sbx_ctx* ctx, CUstream stream, bool force_table = false) {
         if (ctx->hash_tab) { ctx->cu->StreamSynchronize(stream); ctx->cu->MemFree(ctx->hash_tab); ctx->hash_tab = 0; }
         ctx->hash_len = 0;
         if (want_len > 0) {
-            SBX_TRY(ctx->cu->MemAlloc(&ctx->hash_tab, (size_t)want_len * 4 * sizeof(float)), "cuMemAlloc(hash table)");
+            SBX_TRY(ctx->cu->MemAlloc(&ctx->hash_tab, (size_t)want_len * 8 * sizeof(float)), "cuMemAlloc(hash table)");
             int lo = -(want_len / 2), len = want_len;
             void* args[] = {&ctx->hash_tab, &lo, &len, &ctx->lut};
             SBX_TRY(ctx->cu->LaunchKernel(ctx->k_hash, (unsigned)((len + 255) / 256), 1, 1, 256, 1, 1,
@@ -475,7 +475,7 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
     L.hash_tab = (const float4*)ctx->hash_tab;
     L.hash_bias = SBX_HASH_MAGIC_BITS + ctx->hash_lo;
     L.hash_len = ctx->hash_len;
-    L.hash_span = ctx->hash_len > 113 ? ctx->hash_len - 113 : 0;
+    L.hash_span = ctx->hash_len;
     L.lut = (const void*)ctx->lut;
 
     kernel_image* img = ctx->current;
@@ -669,7 +669,7 @@ int sbx_eval_op(sbx_ctx* ctx, const char* op, const float* in, int in_stride, fl
     L.hash_tab = (const float4*)ctx->hash_tab;
     L.hash_bias = SBX_HASH_MAGIC_BITS + ctx->hash_lo;
     L.hash_len = ctx->hash_len;
-    L.hash_span = ctx->hash_len > 113 ? ctx->hash_len - 113 : 0;
+    L.hash_span = ctx->hash_len;
     L.lut = (const void*)ctx->lut;
     int rc = SBX_OK;
     do {

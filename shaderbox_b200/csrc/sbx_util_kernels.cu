@@ -19,13 +19,15 @@ __device__ __forceinline__ float sbx_hash_of(float n) {
     const float s = sbx_sinf(n) * 753.5453123f;
     return s - floorf(s);
 }
-// tab[k] = { h(n), h(n+1), h(n+157), h(n+158) }, n = lo + k: one z-slice of a noise_iq cell per entry
+// entry k = the eight corners of the noise_iq cell with base index n = lo + k, z-neighbours adjacent
+// (layout and rationale: include/sbx/noise_iq.h)
 extern "C" __global__ void sbx_hash_table_kernel(float4* tab, int lo, int len, const void* lut) {
     sbx_util_stage_lut(lut);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= len) return;
     const float n = (float)(lo + k);
-    tab[k] = make_float4(sbx_hash_of(n), sbx_hash_of(n + 1.0f), sbx_hash_of(n + 157.0f), sbx_hash_of(n + 158.0f));
+    tab[2 * k] = make_float4(sbx_hash_of(n), sbx_hash_of(n + 113.0f), sbx_hash_of(n + 1.0f), sbx_hash_of(n + 114.0f));
+    tab[2 * k + 1] = make_float4(sbx_hash_of(n + 157.0f), sbx_hash_of(n + 270.0f), sbx_hash_of(n + 158.0f), sbx_hash_of(n + 271.0f));
 }
 
 // part -> frame: local row lr of shard (stripe, parts, part) is frame row y

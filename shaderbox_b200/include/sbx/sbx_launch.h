@@ -17,12 +17,12 @@ typedef struct sbx_launch {
     int local_rows;             /* rows rendered by this launch */
     int tiles_x, tiles_y;       /* warp tiles covering width x local_rows */
     float* out;                 /* local_rows * width float4, compacted */
-    /* memoised lattice hash (noise_iq.h): hash_tab[k] = { h(n), h(n+1), h(n+157), h(n+158) },
-       n = hash_lo + k, 0 <= k < hash_len */
+    /* memoised lattice hash (noise_iq.h): entry k = 2 float4 = the 8 corners of the noise_iq cell with base
+       index n = hash_lo + k:  { h(n), h(n+113), h(n+1), h(n+114) }, { h(n+157), h(n+270), h(n+158), h(n+271) } */
     const float4* hash_tab;
     int hash_bias;              /* SBX_HASH_MAGIC_BITS + hash_lo */
-    int hash_len;
-    int hash_span;              /* hash_len - 113: base indices k whose second z-slice k+113 is tabulated too */
+    int hash_len;               /* entries */
+    int hash_span;              /* == hash_len (every entry is a self-contained cell) */
     int out_is_frame;           /* 0: out rows are this launch's local (compacted) rows; 1: out is the FULL frame
                                    (possibly a peer GPU's, mapped over NVLink) and rows land at their frame row */
     const void* lut;            /* SBX_LUT_MATH_BYTES of exp2/log2 tables in global memory (sbx_math.h) */

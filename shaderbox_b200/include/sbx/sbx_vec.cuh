@@ -144,6 +144,29 @@ SBX_FN vec4 operator-(const vec4& a) { return vec4(-a.x, -a.y, -a.z, -a.w); }
 SBX_COMPOUND(vec2) SBX_COMPOUND(vec3) SBX_COMPOUND(vec4)
 #undef SBX_COMPOUND
 
+// ---- packed fp32 pairs (sm_100a FFMA2: one issue slot, two IEEE binary32 operations) ----------
+// The march loops are instruction-issue bound (profiles/), and FFMA2 is the only packed fp32
+// instruction Blackwell has, so every packed operation is phrased as an fma:
+//     a*b   = fma(a, b, -0)      exact: adding -0 changes nothing, including the sign of a zero
+//     a+b   = fma(a, 1, b)       a-b = fma(b, -1, a)
+// each rounding ONCE, exactly like the scalar operation it replaces.  The constants 1, -0, -1 are
+// read from __constant__ memory the compiler cannot see through: ptxas 12.9 contracts
+// mul.rn.f32x2 + add.rn.f32x2 (and fma(fma(a,b,-0),1,c)) into ONE FFMA2 even under -fmad=false
+// (tools/ubench/f32x2.cu), which would change the rounding; with opaque constants no
+// multiply/add pair is visible to it.  pk_fma is a genuine fused multiply-add.
+__constant__ float sbx_pk_const[4] = {1.0f, -0.0f, -1.0f, 0.0f};
+SBX_FN float2 pk(float a, float b) { return make_float2(a, b); }
+SBX_FN float2 pk(float a) { return make_float2(a, a); }
+SBX_FN float2 pk_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+SBX_FN float2 pk_mul(float2 a, float2 b) { return __ffma2_rn(a, b, pk(sbx_pk_const[1])); }
+SBX_FN float2 pk_mul(float2 a, float b) { return __ffma2_rn(a, pk(b), pk(sbx_pk_const[1])); }
+SBX_FN float2 pk_add(float2 a, float2 b) { return __ffma2_rn(a, pk(sbx_pk_const[0]), b); }
+SBX_FN float2 pk_sub(float2 a, float2 b) { return __ffma2_rn(b, pk(sbx_pk_const[2]), a); }
+SBX_FN float2 pk_one_minus(float2 a) { return __ffma2_rn(a, pk(sbx_pk_const[2]), pk(1.0f)); }
+// x*(1-a) + y*a per lane, (1-a) given: the body of mix() (three roundings per lane)
+SBX_FN float2 pk_mix(float2 x, float2 y, float one_minus_a, float a) { return pk_add(pk_mul(x, one_minus_a), pk_mul(y, a)); }
+SBX_FN float2 pk_mix(float2 x, float2 y, float2 one_minus_a, float2 a) { return pk_add(pk_mul(x, one_minus_a), pk_mul(y, a)); }
+
 // ---- scalar builtins --------------------------------------------------------------------------
 SBX_FN float sin(float a) { return sbx_sinf(a); }
 SBX_FN float cos(float a) { return sbx_cosf(a); }
