@@ -187,7 +187,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=args.json_out, flush=True)
     return 0
 
 
@@ -211,6 +211,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     app, w, h, t, ov = WORKLOADS[args.workload]
@@ -368,7 +369,7 @@ def run_ours(args):
             cb = cpu_reference_rate(args.workload, budget_s=args.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["fp32_issue"] = fp32_issue(args.workload, avg_kernel_ms, sm_max_mhz, clocks)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=args.json_out, flush=True)
     if shared is not None:
         shared.close()
     r.close()
@@ -413,6 +414,15 @@ def fp32_issue(workload, kernel_ms, sm_max_mhz, clocks):
                     "hash(n) calls served by the memo table still count as the reference's sin" % rows}
 
 
+def _stdout_for_json_only():
+    """Libraries underneath (NCCL's version banner) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for everything else and keep a private handle on the real stdout."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -428,6 +438,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: render in HBM and copy instead of storing into the host frame")
     args = ap.parse_args()
+    args.json_out = _stdout_for_json_only()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)

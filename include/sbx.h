@@ -84,6 +84,7 @@ typedef struct sbx_timing {
     int   launches;      /* kernels launched by the last call */
     int   grid_blocks, block_threads, regs_per_thread, blocks_per_sm;
     int   zero_copy;     /* 1 if sbx_render_host stored straight into a pinned+mapped host frame */
+    int   lanes_per_pixel; /* 1, or P for a cooperative image (P lanes share one pixel's march) */
 } sbx_timing;
 
 typedef struct sbx_ctx sbx_ctx;
@@ -148,7 +149,9 @@ int sbx_frame_read(sbx_ctx* ctx, const float* dev, float* host, size_t bytes, vo
 int sbx_unshard_device(sbx_ctx* ctx, int width, int height, const sbx_shard* shard,
                        const float* dev_part, float* dev_frame, void* stream);
 
-/* Options: "use_hash_table" 0|1, "hash_table_log2" 9..22 (noise_iq memo table), "host_zero_copy" 0|1. */
+/* Options: "use_hash_table" 0|1, "hash_table_log2" 9..22 (noise_iq memo table), "host_zero_copy" 0|1,
+ * "coop_waves_x100" W (default 250): with the default variant, launches smaller than W/100 waves of resident warps
+ * use the app's cooperative image (several lanes per pixel) if one is shipped; 0 = never. */
 int sbx_set_option(sbx_ctx* ctx, const char* key, int value);
 
 int sbx_last_timing(sbx_ctx* ctx, sbx_timing* out);

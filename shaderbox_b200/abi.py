@@ -57,6 +57,7 @@ class Timing(C.Structure):
         ("regs_per_thread", C.c_int),
         ("blocks_per_sm", C.c_int),
         ("zero_copy", C.c_int),
+        ("lanes_per_pixel", C.c_int),
     ]
 
 

@@ -234,6 +234,73 @@ SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-202
     return vec4(radiance, radiance, radiance, alpha * smoothstep(.0f, .2f, cutoff));
 }
 
+#if SBX_LANES_PER_PIXEL > 1
+// Cooperative march (image built with -DSBX_LANES_PER_PIXEL=P): the P lanes of a pixel take the
+// view-march steps i = r*P + phase of round r.  Everything expensive in a step -- its density,
+// its Beer-Lambert factor T_i and its light march -- depends only on the step's position, not on
+// the accumulators, so the lanes evaluate P steps of the SAME ray at once; the accumulators
+// (transmittance, radiance, alpha; :138-147) are then updated in step order from warp shuffles,
+// redundantly in all P lanes, with the reference's operations.  Steps evaluated past the
+// alpha > .999 exit (:197) are discarded.  A ray's work is spread over P times as many warps, each
+// P times shorter: frames that are small for the machine (one GPU's share of a 1080p frame at 8
+// GPUs is ~2 waves of warps) no longer end in a long single-warp tail, and the lanes of a warp
+// sit on neighbouring steps of the same rays, which keeps their branches and table lines together.
+SBX_FN vec4 render_clouds_coop(_in(ray_t) eye, bool active) {
+    const int P = SBX_LANES_PER_PIXEL;
+    const int lane = threadIdx.x & 31, phase = lane % P, base = lane - phase;
+    const vec3 projection = eye.direction / eye.direction.y;
+    vec3 origin = eye.origin + projection * 150.0f;
+    origin += wind_dir * u_time * (1.0f / cld_noise_factor);
+
+    sbx_cov = 1.0f - cld_coverage;
+    const float band = (sbx_cov + .0135f) - sbx_cov;
+    sbx_band_lo = band > 0.0f ? 0.0f : -__int_as_float(0x7f800000);
+    sbx_band_hi = band > 0.0f ? band : __int_as_float(0x7f800000);
+    sbx_phase = henyey_greenstein_phase_func(clamp(dot(sun_dir, eye.direction), 0.0f, 1.0f));
+
+    const float2 origin_xy = pk(origin.x, origin.y), proj_xy = pk(projection.x, projection.y);
+    float transmittance = 1.0f, radiance = 0.0f, alpha = 0.0f;
+    const float dt = cld_thick / float(cld_march_steps);
+    const int steps = cld_march_steps;
+    float t = 0.0f;                                    // the reference's t of step `phase`: 0 (+ dt) (+ dt) ...
+    for (int q = 0; q < phase; ++q) t += dt;
+    bool done = !active;
+    for (int r = 0; r * P < steps; ++r) {
+        if (__all_sync(0xffffffffu, done)) break;
+        const int i = r * P + phase;
+        float T_i = 2.0f, A = 0.0f;                    // T_i = 2 (impossible for exp(-x), x >= 0): the step integrates nothing
+        if (!done && i < steps) {
+            const float2 pos_xy = pk_add(origin_xy, pk_mul(proj_xy, t));
+            const float pos_z = origin.z + t * projection.z;
+            const float density = density_view(pos_xy, pos_z);
+            if (!(density < .005f)) {
+                T_i = exp(-density * sigma_scattering * dt);
+                A = (density * sigma_scattering) * illuminate_volume(pos_xy, pos_z, sun_dir);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < P; ++q) t += dt;           // this lane's next step is P steps on
+        if (__any_sync(0xffffffffu, T_i != 2.0f)) {    // rounds in which no lane of the warp met cloud change nothing
+#pragma unroll
+            for (int q = 0; q < P; ++q) {              // steps r*P .. r*P+P-1 in order
+                const float Tq = __shfl_sync(0xffffffffu, T_i, base + q);
+                const float Aq = __shfl_sync(0xffffffffu, A, base + q);
+                if (!done && Tq != 2.0f) {
+                    transmittance *= Tq;
+                    radiance += Aq * transmittance * dt;
+                    alpha += (1.0f - Tq) * (1.0f - alpha);
+                    if (alpha > .999f) done = true;    // :197 (alpha only changes in a cloud step)
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = P / 2; off > 0; off >>= 1) sbx_kmax = ::max(sbx_kmax, __shfl_xor_sync(0xffffffffu, sbx_kmax, off));
+    const float cutoff = dot(eye.direction, vec3(0.0f, 1.0f, 0.0f));
+    return vec4(radiance, radiance, radiance, alpha * smoothstep(.0f, .2f, cutoff));
+}
+#endif
+
 // ---- the generic path: the app as written (:62-202) on the library's noise_iq / fbm, which fall
 // back to the arithmetic hash outside the memo table.  Cold code: runs only for a pixel whose fast
 // path met a lattice index outside the table (huge u_time * wind_dir, or the table switched off).
@@ -286,9 +353,15 @@ static __device__ __noinline__ float4 sbx_generic_pixel(const sbx_launch* L, flo
 
 SBX_FN vec3 render(_in(ray_t) eye_ray, _in(vec3) point_cam) {   // :204-218
     const vec3 sky = render_sky_color(eye_ray.direction);
-    if (dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f) return sky;
     sbx_kmax = 0u;
+#if SBX_LANES_PER_PIXEL > 1
+    const bool below = dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f;
+    vec4 cld = render_clouds_coop(eye_ray, !below);                     // every lane of the warp takes part in the shuffles
+    if (below) return sky;
+#else
+    if (dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f) return sky;
     vec4 cld = render_clouds(eye_ray);
+#endif
     if (sbx_kmax >= (unsigned)sbx_L->hash_span) {                       // table miss: redo the pixel
         const float4 g = sbx_generic_pixel(sbx_L, eye_ray.origin.x, eye_ray.origin.y, eye_ray.origin.z,
                                            eye_ray.direction.x, eye_ray.direction.y, eye_ray.direction.z);

@@ -40,6 +40,7 @@ struct driver_api {
     CUresult (*ModuleLoadData)(CUmodule*, const void*);
     CUresult (*ModuleUnload)(CUmodule);
     CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
+    CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*);
     CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction);
     CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t);
@@ -90,6 +91,7 @@ driver_api* load_driver(std::string* err) {
     SBX_SYM(ModuleLoadData, "cuModuleLoadData")
     SBX_SYM(ModuleUnload, "cuModuleUnload")
     SBX_SYM(ModuleGetFunction, "cuModuleGetFunction")
+    SBX_SYM(ModuleGetGlobal, "cuModuleGetGlobal_v2")
     SBX_SYM(FuncGetAttribute, "cuFuncGetAttribute")
     SBX_SYM(FuncSetAttribute, "cuFuncSetAttribute")
     SBX_SYM(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
@@ -121,6 +123,7 @@ struct kernel_image {
     CUfunction render = nullptr;
     int regs = 0, max_threads = 0, blocks_per_sm = 0;
     int warps_per_cta = 4;
+    int tile_w = SBX_TILE_W, tile_h = SBX_TILE_H, lanes_per_pixel = 1;   // sbx_image_info of the image
     std::string variant;
 };
 
@@ -146,6 +149,7 @@ struct sbx_ctx {
 
     std::map<std::string, kernel_image> images;   // "APP_X/variant"
     kernel_image* current = nullptr;
+    kernel_image* current_coop = nullptr;   // cooperative image of the same app (P lanes per pixel), for small grids
     std::string current_app;
 
     CUmodule util_module = nullptr;
@@ -157,6 +161,7 @@ struct sbx_ctx {
     int opt_hash_log2 = 18;       // table covers [-2^(k-1), 2^(k-1))
     int opt_use_hash = 1;
     int opt_zero_copy = 1;        // sbx_render_host: store straight into pinned+mapped host frames
+    int opt_coop_waves_x100 = 250;   // use the cooperative image when the grid is below this many waves of resident warps
 
     CUdeviceptr frame = 0;        // internal frame for sbx_render_host
     size_t frame_bytes = 0;
@@ -248,6 +253,15 @@ int bind_image(sbx_ctx* ctx, const std::string& key, const std::string& cubin, c
     ctx->cu->OccupancyMaxActiveBlocksPerMultiprocessor(&img.blocks_per_sm, img.render, img.warps_per_cta * 32,
                                                        SBX_LUT_MATH_BYTES);
     img.variant = variant;
+    {   // tile geometry the image was compiled for (sbx_kernel.cuh); images without the symbol use the default 8x4
+        CUdeviceptr info = 0;
+        size_t bytes = 0;
+        int v[4] = {0, 0, 0, 0};
+        if (ctx->cu->ModuleGetGlobal(&info, &bytes, img.module, "sbx_image_info") == CUDA_SUCCESS && bytes >= sizeof v &&
+            ctx->cu->MemcpyDtoH(v, info, sizeof v) == CUDA_SUCCESS && v[0] > 0 && v[1] > 0 && v[2] > 0) {
+            img.tile_w = v[0]; img.tile_h = v[1]; img.lanes_per_pixel = v[2];
+        }
+    }
     auto it = ctx->images.find(key);
     if (it != ctx->images.end() && it->second.module) ctx->cu->ModuleUnload(it->second.module);
     ctx->images[key] = img;
@@ -423,7 +437,23 @@ int sbx_load_app(sbx_ctx* ctx, const char* app_name, const char* variant) {
             it = ctx->images.find(key);
         }
         ctx->current = &it->second;
+        ctx->current_coop = nullptr;
         ctx->current_app = app_name;
+        if (!(variant && *variant) && v == "native") {
+            // default selection only: the cooperative build of the same scene kernel, if shipped
+            const std::string ckey = std::string(app_name) + "/coop";
+            auto ct = ctx->images.find(ckey);
+            if (ct == ctx->images.end()) {
+                std::string cbin;
+                if (read_file(sbx::library_dir() + "/images/" + app_name + ".coop.cubin", &cbin) &&
+                    bind_image(ctx, ckey, cbin, "coop") == SBX_OK)
+                    ct = ctx->images.find(ckey);
+            }
+            if (ct != ctx->images.end()) {
+                ctx->current_coop = &ct->second;
+                ctx->current = &ctx->images.find(key)->second;
+            }
+        }
         return SBX_OK;
     }
     return ctx->fail(SBX_ERR_UNKNOWN_APP, "no kernel image for %s (variant %s) under %s/images", app_name,
@@ -445,6 +475,7 @@ int sbx_set_option(sbx_ctx* ctx, const char* key, int value) {
     }
     if (!std::strcmp(key, "use_hash_table")) { ctx->opt_use_hash = value ? 1 : 0; return SBX_OK; }
     if (!std::strcmp(key, "host_zero_copy")) { ctx->opt_zero_copy = value ? 1 : 0; return SBX_OK; }
+    if (!std::strcmp(key, "coop_waves_x100")) { if (value < 0) return SBX_ERR_INVALID; ctx->opt_coop_waves_x100 = value; return SBX_OK; }
     return SBX_ERR_INVALID;
 }
 
@@ -468,8 +499,16 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
     L.part = s.part;
     L.local_rows = shard_rows(s, p->height);
     if (L.local_rows == 0) return SBX_OK;
-    L.tiles_x = (p->width + SBX_TILE_W - 1) / SBX_TILE_W;
-    L.tiles_y = (L.local_rows + SBX_TILE_H - 1) / SBX_TILE_H;
+    kernel_image* img = ctx->current;
+    if (ctx->current_coop) {
+        // A frame (or one rank's share of it) that is only a couple of waves of resident warps ends in a long tail of
+        // single warps still marching; the cooperative image cuts every ray into P shorter pieces (multi-GPU).
+        const long long warps = (long long)((p->width + img->tile_w - 1) / img->tile_w) * ((L.local_rows + img->tile_h - 1) / img->tile_h);
+        const long long resident = (long long)ctx->sm_count * img->blocks_per_sm * img->warps_per_cta;
+        if (warps * 100 < resident * ctx->opt_coop_waves_x100) img = ctx->current_coop;
+    }
+    L.tiles_x = (p->width + img->tile_w - 1) / img->tile_w;
+    L.tiles_y = (L.local_rows + img->tile_h - 1) / img->tile_h;
     L.out = dev_rgba;
     L.out_is_frame = out_is_frame;
     L.hash_tab = (const float4*)ctx->hash_tab;
@@ -478,7 +517,6 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
     L.hash_span = ctx->hash_len;
     L.lut = (const void*)ctx->lut;
 
-    kernel_image* img = ctx->current;
     const long long tiles = (long long)L.tiles_x * L.tiles_y;
     const unsigned grid = (unsigned)((tiles + img->warps_per_cta - 1) / img->warps_per_cta);
     void* args[] = {&L};
@@ -492,6 +530,7 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
     ctx->timing.block_threads = img->warps_per_cta * 32;
     ctx->timing.regs_per_thread = img->regs;
     ctx->timing.blocks_per_sm = img->blocks_per_sm;
+    ctx->timing.lanes_per_pixel = img->lanes_per_pixel;
     ctx->timing.kernel_ms = -1.0f;   // resolved lazily by sbx_last_timing
     ctx->timing.d2h_ms = 0.0f;
     return SBX_OK;

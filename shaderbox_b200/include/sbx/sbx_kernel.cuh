@@ -11,8 +11,13 @@
 //
 // Mapping: one thread per pixel; a warp owns an 8x4 pixel tile (each tile row is one 128-byte
 // line of the RGBA32F frame, so a warp's store is four full lines); a CTA is SBX_WARPS_PER_CTA
-// warps on consecutive tiles.  The prologue stages the math LUT block from HBM to shared memory
-// with one TMA bulk copy (cp.async.bulk) completing on an mbarrier.
+// warps on consecutive tiles.  A scene kernel may instead put SBX_LANES_PER_PIXEL = P > 1 lanes on
+// every pixel (native/app_clouds_native.h splits a ray's march steps over them): the warp tile is
+// then (32/P) x 1 pixels, lane = pixel * P + phase, and only phase 0 stores.  Tiles are issued
+// bottom row first (measured: issuing the top rows first costs APP_CLOUDS 6 % -- its longest rays
+// are the ones just above the horizon, and they should not start last).  The prologue stages the
+// math LUT block from HBM to shared memory with one TMA bulk copy (cp.async.bulk) completing on
+// an mbarrier.
 #ifndef SBX_KERNEL_CUH_
 #define SBX_KERNEL_CUH_
 
@@ -25,6 +30,18 @@
 #ifndef SBX_MIN_CTAS_PER_SM
 #define SBX_MIN_CTAS_PER_SM 1
 #endif
+#ifndef SBX_LANES_PER_PIXEL
+#define SBX_LANES_PER_PIXEL 1
+#endif
+#if SBX_LANES_PER_PIXEL == 1
+#define SBX_IMG_TILE_W SBX_TILE_W
+#define SBX_IMG_TILE_H SBX_TILE_H
+#else
+#define SBX_IMG_TILE_W (32 / SBX_LANES_PER_PIXEL)
+#define SBX_IMG_TILE_H 1
+#endif
+// read by the host at load time (cuModuleGetGlobal): { tile width, tile height, lanes per pixel, 0 }
+extern "C" __device__ const int sbx_image_info[4] = {SBX_IMG_TILE_W, SBX_IMG_TILE_H, SBX_LANES_PER_PIXEL, 0};
 
 // ---- TMA bulk copy of the LUT block: global -> shared, completion on an mbarrier --------------
 __device__ __forceinline__ unsigned sbx_smem_addr(const void* p) {
@@ -95,9 +112,20 @@ sbx_render(const __grid_constant__ sbx_launch L) {
     const int lane = threadIdx.x & 31;
     const int tile_x = warp % L.tiles_x;
     const int tile_y = warp / L.tiles_x;
+#if SBX_LANES_PER_PIXEL == 1
     const int x = tile_x * SBX_TILE_W + (lane & (SBX_TILE_W - 1));
     const int lr = tile_y * SBX_TILE_H + (lane / SBX_TILE_W);
     if (x >= L.p.width || lr >= L.local_rows) return;
+    const bool stores = true;
+#else
+    // P lanes per pixel cooperate through warp shuffles, so every lane of the warp stays: lanes past
+    // the right edge (or in a tile past the last one) render the clamped pixel and store nothing
+    int x = tile_x * SBX_IMG_TILE_W + lane / SBX_LANES_PER_PIXEL;
+    int lr = tile_y;
+    const bool stores = x < L.p.width && lr < L.local_rows && (lane % SBX_LANES_PER_PIXEL) == 0;
+    x = x < L.p.width ? x : L.p.width - 1;
+    lr = lr < L.local_rows ? lr : L.local_rows - 1;
+#endif
 
     // local (compacted) row -> frame row of this shard
     const int y = ((lr / L.stripe_rows) * L.n_parts + L.part) * L.stripe_rows + lr % L.stripe_rows;
@@ -106,8 +134,10 @@ sbx_render(const __grid_constant__ sbx_launch L) {
     sbx_glsl::vec4 c;
     app.mainImage(c, sbx_glsl::vec2(float(x) + 0.5f, float(y) + 0.5f));
 
-    float4* dst = reinterpret_cast<float4*>(L.out) + (size_t)(L.out_is_frame ? y : lr) * (size_t)L.p.width + (size_t)x;
-    __stcs(dst, make_float4(c.x, c.y, c.z, c.w));
+    if (stores) {
+        float4* dst = reinterpret_cast<float4*>(L.out) + (size_t)(L.out_is_frame ? y : lr) * (size_t)L.p.width + (size_t)x;
+        __stcs(dst, make_float4(c.x, c.y, c.z, c.w));
+    }
 }
 
 #endif  // SBX_KERNEL_CUH_

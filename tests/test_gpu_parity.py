@@ -99,6 +99,7 @@ def test_native_clouds_kernel_matches_oracle_over_the_uniform_space(ov, renderer
     w, h, t = 192, 108, 2.5
     want = loader.oracle_render("APP_CLOUDS", abi.default_params(w, h, t, **ov))
     check(renderers("APP_CLOUDS", "native").render(w, h, u_time=t, **ov), want)
+    check(renderers("APP_CLOUDS", "coop").render(w, h, u_time=t, **ov), want)
     check(renderers("APP_CLOUDS", "plugin").render(w, h, u_time=t, **ov), want)
 
 
@@ -109,6 +110,37 @@ def test_native_clouds_far_from_the_origin(t, renderers):
     w, h = 96, 54
     want = loader.oracle_render("APP_CLOUDS", abi.default_params(w, h, t))
     check(renderers("APP_CLOUDS", "native").render(w, h, u_time=t), want)
+    check(renderers("APP_CLOUDS", "coop").render(w, h, u_time=t), want)
+
+
+@pytest.mark.parametrize("steps", [128, 100, 37, 3, 1])
+def test_cooperative_march_equals_one_lane_per_pixel(steps, renderers):
+    """The cooperative image puts 4 lanes on a pixel (march steps i = 4r + phase) and replays the accumulation in
+    step order from shuffles; ragged widths leave lanes without a pixel, step counts leave phases without a step."""
+    for w, h in ((203, 61), (64, 9), (7, 3)):
+        a = renderers("APP_CLOUDS", "native").render(w, h, u_time=1.5, cld_march_steps=steps)
+        b = renderers("APP_CLOUDS", "coop").render(w, h, u_time=1.5, cld_march_steps=steps)
+        assert renderers("APP_CLOUDS", "coop").timing()["lanes_per_pixel"] == 4
+        assert bits_equal(a, b), (w, h, steps, diff_report(a, b))
+        sh = (4, 8, 5)
+        assert bits_equal(renderers("APP_CLOUDS", "coop").render(w, h, u_time=1.5, cld_march_steps=steps, shard=sh),
+                          a[abi.shard_rows(*sh, h)])
+
+
+def test_default_variant_picks_the_cooperative_image_for_small_grids(renderers):
+    r = renderers("APP_CLOUDS", None)
+    big = r.render(1920, 1080, u_time=1.5)
+    assert r.timing()["lanes_per_pixel"] == 1
+    part = r.render(1920, 1080, u_time=1.5, shard=(4, 8, 3))          # one rank's share at 8 GPUs: ~2 waves of warps
+    assert r.timing()["lanes_per_pixel"] == 4
+    assert bits_equal(part, big[abi.shard_rows(4, 8, 3, 1080)])
+    r.set_option("coop_waves_x100", 0)
+    try:
+        part1 = r.render(1920, 1080, u_time=1.5, shard=(4, 8, 3))
+        assert r.timing()["lanes_per_pixel"] == 1
+    finally:
+        r.set_option("coop_waves_x100", 250)
+    assert bits_equal(part1, part)
 
 
 @pytest.mark.parametrize("variant", ["plugin", "native"])
