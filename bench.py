@@ -221,7 +221,11 @@ def run_ours(args):
     shard = multi.shard_of(rank, world, stripe)
     rows = multi.part_rows(h, shard)
     stream = torch.cuda.current_stream(dev)
-    part = torch.empty((rows, w, 4), dtype=torch.float32, device=dev)
+    rgba8 = args.format == "rgba8"
+    if rgba8 and world > 1:
+        raise SystemExit("bench.py: --format rgba8 is a 1-GPU measurement")
+    part = torch.empty((rows, w, 4), dtype=torch.uint8 if rgba8 else torch.float32, device=dev)
+    px_bytes = 4 if rgba8 else 16
     frame = torch.empty((h, w, 4), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
     fused = world > 1 and args.gather == "p2p"
     shared = multi.SharedFrame(r, w, h) if fused else None
@@ -231,7 +235,7 @@ def run_ours(args):
     def step():
         """kernel (+ gather + unshard at N > 1), all on `stream`"""
         if world == 1:
-            r.render_into(p, part.data_ptr(), shard=shard, stream=stream.cuda_stream)
+            (r.render_rgba8_into if rgba8 else r.render_into)(p, part.data_ptr(), shard=shard, stream=stream.cuda_stream)
         elif fused:
             shared.render(p, stripe)
         else:
@@ -293,11 +297,11 @@ def run_ours(args):
     if args.no_zero_copy:
         r.set_option("host_zero_copy", 0)
     if world == 1:
-        host = torch.empty((rows, w, 4), dtype=torch.float32).pin_memory()
+        host = torch.empty((rows, w, 4), dtype=torch.uint8 if rgba8 else torch.float32).pin_memory()
 
         def e2e_step():
-            r.render_host_ptr(p, host.data_ptr(), shard=shard)        # sbx_render_host: synchronous
-        d2h_bytes = int(16 * rows * w)
+            (r.render_rgba8_host_ptr if rgba8 else r.render_host_ptr)(p, host.data_ptr(), shard=shard)   # sbx_render_host[_rgba8]: synchronous
+        d2h_bytes = int(px_bytes * rows * w)
     else:
         # N ranks: the frame is assembled on rank 0 (fused P2P stores or NCCL gather), then read back to the host there
         host = torch.empty((h, w, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
@@ -332,7 +336,7 @@ def run_ours(args):
         px = w * h
         value = px * args.steps / (total_ms * 1e-3) * 1e-6
         avg_kernel_ms = total_kernel_ms / args.steps
-        alg_bytes = 16.0 * rows * w                       # this rank's launch: 16 B/pixel written, 0 read
+        alg_bytes = float(px_bytes) * rows * w            # this rank's launch: 16 (RGBA32F) or 4 (RGBA8) B/pixel written, 0 read
         achieved = alg_bytes / (avg_kernel_ms * 1e-3) * 1e-9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -342,7 +346,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s %dx%d u_time=%g %s" % (app, w, h, t, json.dumps(ov)), "variant": tm_variant(r, args),
+            "config": {"workload": "%s %dx%d u_time=%g %s" % (app, w, h, t, json.dumps(ov)), "variant": tm_variant(r, args), "format": "RGBA8_UNORM" if rgba8 else "RGBA32F",
                        "l2": "flushed between steps (256 MiB memset on the same stream, outside the timed events); the frame is write-only",
                        "sharding": "none" if world == 1 else (
                            "%d-row stripes round-robin over %d ranks; every rank's render kernel stores its rows into rank 0's frame over NVLink "
@@ -434,6 +438,8 @@ def main():
     ap.add_argument("--stripe-rows", type=int, default=4)
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = render kernels store into rank 0's frame over NVLink; nccl = compacted parts + ncclGather + unshard")
+    ap.add_argument("--format", default="f32", choices=["f32", "rgba8"],
+                    help="frame format: raw float4 (BASELINE.json) or the 8-bit swap-chain format of the reference's presenting hosts")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: render in HBM and copy instead of storing into the host frame")

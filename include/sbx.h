@@ -125,6 +125,18 @@ int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_
 int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
                     float* host_rgba);
 
+/* The 8-bit output of the reference's presenting hosts.  hlsltoy renders mainImage's colour (already
+ * sRGB-encoded by src/main.h:52 linear_to_srgb) into a DXGI_FORMAT_R8G8B8A8_UNORM swap chain
+ * (util/hlsltoy/src/hlsltoy.cpp:192); the FLOAT -> UNORM rule of that target is: NaN -> 0, clamp to [0, 1],
+ * multiply by 255, add 0.5, truncate.  These entry points apply it inside the render kernel's store (one
+ * 32-bit store per pixel, R in the low byte; a quarter of the frame bytes to HBM / over PCIe).  Frames are
+ * rows*width*4 bytes, same row order and sharding as the float entry points; host frames may be pinned+mapped
+ * (zero-copy) or pageable. */
+int sbx_render_device_rgba8(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
+                            unsigned char* dev_rgba8, void* stream);
+int sbx_render_host_rgba8(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
+                          unsigned char* host_rgba8);
+
 /* Render the rows of `shard` straight into a FULL frame (height*width float4) at their frame rows --
  * no compaction, no gather, no unshard.  dev_frame may live on ANOTHER GPU of the box (a pointer
  * obtained from sbx_frame_import): the kernel's float4 stores then travel over NVLink while the

@@ -29,7 +29,6 @@
 //    stays in its lattice cell is one floor, one smoothstep weight and one mix; an octave that
 //    crossed into the next cell is re-sliced alone.  Equality is checked on the values, per sample
 //    and per octave, so any sun direction stays exact; it just re-slices every octave.
-//  * exp(-0 * sigma * dt) == 1 exactly: empty light-march samples skip the exponential (:110-113).
 //  * the Henyey-Greenstein factor of illuminate_volume (:121) depends only on the ray, not on the
 //    sample: one pow per ray instead of one per in-cloud step.
 //  * table misses are deferred: lattice indices are clamped into the memo table and the largest
@@ -113,13 +112,19 @@ SBX_FN float density_view(float2 pos_xy, float pos_z) {
     const float guard = 1e-5f;
     sbx_mx = pos_xy.x; sbx_my = pos_xy.y;
     float t = sbx_octave(pxy, pz, sbx_mz0, sbx_ys0) * .5f;            // 0 + n*.5 == n*.5 (n >= +0)
+#ifndef SBX_X_NOLAZY
     if (t <= sbx_cov - .4375f - guard) return 0.0f;
+#endif
     pxy = pk_mul(pxy, 2.64f); pz *= 2.64f;
     t += sbx_octave(pxy, pz, sbx_mz1, sbx_ys1) * .25f;
+#ifndef SBX_X_NOLAZY
     if (t <= sbx_cov - .1875f - guard) return 0.0f;
+#endif
     pxy = pk_mul(pxy, 2.64f); pz *= 2.64f;
     t += sbx_octave(pxy, pz, sbx_mz2, sbx_ys2) * .125f;
+#ifndef SBX_X_NOLAZY
     if (t <= sbx_cov - .0625f - guard) return 0.0f;
+#endif
     pxy = pk_mul(pxy, 2.64f); pz *= 2.64f;
     t += sbx_octave(pxy, pz, sbx_mz3, sbx_ys3) * .0625f;
     return sbx_density_of(t);
@@ -190,7 +195,7 @@ SBX_FN float illuminate_volume(float2 origin_xy, float origin_z, _in(vec3) L) {
 #ifdef SBX_X_NOEXP
         if (density != 0.0f) transmittance *= (1.0f - density * sigma_scattering * dt);
 #else
-        if (density != 0.0f) transmittance *= exp(-density * sigma_scattering * dt);   // exp(-0) == 1
+        transmittance *= exp(-density * sigma_scattering * dt);   // branch-free: an empty sample multiplies by exp(-0) == 1
 #endif
         pos_xy = pk_add(pos_xy, pk(step.x, step.y));
         pos_z += step.z;

@@ -4,21 +4,53 @@
 //
 //   sbx_cli compile <app_header.h> <APP_NAME> <out.cubin>      (needs no GPU)
 //   sbx_cli render  <APP_NAME> <width> <height> <u_time> <out.rgba32f> [--variant native|plugin]
-//                   [--steps N] [--frames K] [--device D]
-// `render` prints one JSON line with the kernel time of the last frame.
+//                   [--steps N] [--frames K] [--device D] [--ppm out.ppm] [--rgba8 out.rgba8]
+//   sbx_cli flatten <file.h>                                   (needs no GPU)
+// `render` prints one JSON line with the kernel time of the last frame.  --ppm / --rgba8 render the
+// frame again through the 8-bit path (sbx_render_host_rgba8: what the reference's presenting hosts
+// show, util/hlsltoy/src/hlsltoy.cpp:192) and write it as a binary PPM (top row first) / raw bytes.
+// `flatten` is the reference's include expander (util/inclxpnd/src/inclxpnd.cpp:8-41): prints the
+// file with every `#include "x"` / `#include <x>` line replaced, recursively, by the contents of x
+// (resolved against the current directory, as the reference does); a missing file prints
+// "*** error: cannot include file: x" in its place.  It is how an app header is made pasteable
+// into shadertoy (README.md:29-32).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
 #include <string>
 #include <vector>
 
 #include "../../include/sbx.h"
 
+// util/inclxpnd/src/inclxpnd.cpp:8-41 -- same tokenisation (first whitespace-separated token == "#include",
+// second token quoted with "" or <>), same error codes (2: token too short, 3: not quoted)
+static int flatten(std::istream& in, std::ostream& out) {
+    for (std::string line; std::getline(in, line);) {
+        std::istringstream tok(line);
+        std::string word;
+        tok >> word;
+        if (word != "#include") { out << line << std::endl; continue; }
+        word.clear();
+        tok >> word;
+        if (word.length() < 2) return 2;
+        if ((word.front() != '"' && word.front() != '<') || (word.back() != '"' && word.back() != '>')) return 3;
+        const std::string name(word.begin() + 1, word.end() - 1);
+        std::ifstream inc(name);
+        if (inc.good()) flatten(inc, out);
+        else out << "*** error: cannot include file: " << name << std::endl;
+    }
+    return 0;
+}
+
 static int usage() {
     fprintf(stderr,
             "usage: sbx_cli compile <app_header.h> <APP_NAME> <out.cubin>\n"
             "       sbx_cli render <APP_NAME> <width> <height> <u_time> <out.rgba32f|-> [--variant v] [--steps n] "
-            "[--frames k] [--device d]\n");
+            "[--frames k] [--device d] [--ppm out.ppm] [--rgba8 out.rgba8]\n"
+            "       sbx_cli flatten <file.h>\n");
     return 2;
 }
 
@@ -33,6 +65,12 @@ int main(int argc, char** argv) {
         printf("{\"compiled\": \"%s\", \"app\": \"%s\", \"image\": \"%s\"}\n", argv[2], argv[3], argv[4]);
         return 0;
     }
+    if (!strcmp(argv[1], "flatten")) {
+        if (argc < 3) return usage();
+        std::ifstream in(argv[2]);
+        if (!in.good()) return 1;
+        return flatten(in, std::cout);
+    }
     if (!strcmp(argv[1], "render")) {
         if (argc < 7) return usage();
         const char* app = argv[2];
@@ -40,12 +78,16 @@ int main(int argc, char** argv) {
         const float t = (float)atof(argv[5]);
         const char* out_path = argv[6];
         const char* variant = nullptr;
+        const char* ppm_path = nullptr;
+        const char* rgba8_path = nullptr;
         int steps = 0, frames = 1, device = 0;
         for (int i = 7; i + 1 < argc; i += 2) {
             if (!strcmp(argv[i], "--variant")) variant = argv[i + 1];
             else if (!strcmp(argv[i], "--steps")) steps = atoi(argv[i + 1]);
             else if (!strcmp(argv[i], "--frames")) frames = atoi(argv[i + 1]);
             else if (!strcmp(argv[i], "--device")) device = atoi(argv[i + 1]);
+            else if (!strcmp(argv[i], "--ppm")) ppm_path = argv[i + 1];
+            else if (!strcmp(argv[i], "--rgba8")) rgba8_path = argv[i + 1];
             else return usage();
         }
         sbx_ctx* ctx = nullptr;
@@ -69,6 +111,29 @@ int main(int argc, char** argv) {
             if (!fp) { perror(out_path); return 1; }
             fwrite(frame.data(), sizeof(float), frame.size(), fp);
             fclose(fp);
+        }
+        if (ppm_path || rgba8_path) {
+            std::vector<unsigned char> px((size_t)w * h * 4);
+            st = sbx_render_host_rgba8(ctx, &p, nullptr, px.data());
+            if (st != SBX_OK) { fprintf(stderr, "sbx_render_host_rgba8: %s: %s\n", sbx_strerror(st), sbx_last_error(ctx)); return 1; }
+            if (rgba8_path) {
+                FILE* fp = fopen(rgba8_path, "wb");
+                if (!fp) { perror(rgba8_path); return 1; }
+                fwrite(px.data(), 1, px.size(), fp);
+                fclose(fp);
+            }
+            if (ppm_path) {   // P6, top row first: frame row 0 is the BOTTOM row (fragCoord.y = 0.5)
+                FILE* fp = fopen(ppm_path, "wb");
+                if (!fp) { perror(ppm_path); return 1; }
+                fprintf(fp, "P6\n%d %d\n255\n", w, h);
+                std::vector<unsigned char> row((size_t)w * 3);
+                for (int y = h - 1; y >= 0; --y) {
+                    const unsigned char* src = px.data() + (size_t)y * w * 4;
+                    for (int x = 0; x < w; ++x) { row[3 * x] = src[4 * x]; row[3 * x + 1] = src[4 * x + 1]; row[3 * x + 2] = src[4 * x + 2]; }
+                    fwrite(row.data(), 1, row.size(), fp);
+                }
+                fclose(fp);
+            }
         }
         printf("{\"app\": \"%s\", \"width\": %d, \"height\": %d, \"u_time\": %g, \"kernel_ms\": %.4f, \"d2h_ms\": %.4f, "
                "\"mpix_per_s\": %.2f, \"grid\": %d, \"block\": %d, \"regs\": %d, \"ctas_per_sm\": %d}\n",

@@ -480,7 +480,7 @@ int sbx_set_option(sbx_ctx* ctx, const char* key, int value) {
 }
 
 static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_rgba, void* stream_,
-                         int out_is_frame) {
+                         int out_is_frame, int out_rgba8 = 0) {
     if (!ctx || !p || !dev_rgba || p->width <= 0 || p->height <= 0) return SBX_ERR_INVALID;
     if (!ctx->current) return ctx->fail(SBX_ERR_UNKNOWN_APP, "sbx_load_app was not called");
     sbx_shard s;
@@ -511,6 +511,7 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
     L.tiles_y = (L.local_rows + img->tile_h - 1) / img->tile_h;
     L.out = dev_rgba;
     L.out_is_frame = out_is_frame;
+    L.out_rgba8 = out_rgba8;
     L.hash_tab = (const float4*)ctx->hash_tab;
     L.hash_bias = SBX_HASH_MAGIC_BITS + ctx->hash_lo;
     L.hash_len = ctx->hash_len;
@@ -538,7 +539,7 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
 
 // Device-visible alias of a host frame, if the caller's buffer is pinned and mapped (cudaHostAlloc /
 // cuMemHostAlloc / a pinned torch tensor): 0 otherwise.
-static CUdeviceptr mapped_host_alias(sbx_ctx* ctx, float* host) {
+static CUdeviceptr mapped_host_alias(sbx_ctx* ctx, const void* host) {
     unsigned mem_type = 0;
     if (ctx->cu->PointerGetAttribute(&mem_type, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)(uintptr_t)host) != CUDA_SUCCESS)
         return 0;
@@ -609,19 +610,20 @@ int sbx_frame_read(sbx_ctx* ctx, const float* dev, float* host, size_t bytes, vo
     return SBX_OK;
 }
 
-int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* host_rgba) {
-    if (!ctx || !p || !host_rgba || p->width <= 0 || p->height <= 0) return SBX_ERR_INVALID;
+// one frame to host memory, float4 or packed 8-bit pixels
+static int render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, void* host, int rgba8) {
+    if (!ctx || !p || !host || p->width <= 0 || p->height <= 0) return SBX_ERR_INVALID;
     sbx_shard s;
     if (!valid_shard(shard, &s)) return ctx->fail(SBX_ERR_INVALID, "bad shard");
-    const size_t bytes = (size_t)shard_rows(s, p->height) * (size_t)p->width * 4 * sizeof(float);
+    const size_t bytes = (size_t)shard_rows(s, p->height) * (size_t)p->width * (rgba8 ? 4 : 4 * sizeof(float));
     if (bytes == 0) return SBX_OK;
     CUdeviceptr alias = 0;
     {
         ctx_scope scope(ctx);
-        // Pinned + mapped destination: the kernel's float4 stores go straight over PCIe into the
+        // Pinned + mapped destination: the kernel's pixel stores go straight over PCIe into the
         // caller's frame while other pixels are still marching (the frame is write-only and each warp
-        // writes whole 128-byte lines), so there is no separate device->host copy to wait for.
-        if (ctx->opt_zero_copy && ((uintptr_t)host_rgba & 15u) == 0) alias = mapped_host_alias(ctx, host_rgba);
+        // writes whole lines / sectors), so there is no separate device->host copy to wait for.
+        if (ctx->opt_zero_copy && ((uintptr_t)host & 15u) == 0) alias = mapped_host_alias(ctx, host);
         if (!alias && bytes > ctx->frame_bytes) {
             if (ctx->frame) ctx->cu->MemFree(ctx->frame);
             ctx->frame = 0;
@@ -630,16 +632,29 @@ int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, f
             ctx->frame_bytes = bytes;
         }
     }
-    int st = sbx_render_device(ctx, p, &s, (float*)(alias ? alias : ctx->frame), nullptr);
+    int st = render_launch(ctx, p, &s, (float*)(alias ? alias : ctx->frame), nullptr, 0, rgba8);
     if (st != SBX_OK) return st;
     ctx_scope scope(ctx);
-    if (!alias) SBX_TRY(ctx->cu->MemcpyDtoHAsync(host_rgba, ctx->frame, bytes, nullptr), "cuMemcpyDtoHAsync");
+    if (!alias) SBX_TRY(ctx->cu->MemcpyDtoHAsync(host, ctx->frame, bytes, nullptr), "cuMemcpyDtoHAsync");
     SBX_TRY(ctx->cu->EventRecord(ctx->ev2, nullptr), "cuEventRecord");
     SBX_TRY(ctx->cu->StreamSynchronize(nullptr), "cuStreamSynchronize");
     float ms = 0.0f;
     if (ctx->cu->EventElapsedTime(&ms, ctx->ev1, ctx->ev2) == CUDA_SUCCESS) ctx->timing.d2h_ms = ms;
     ctx->timing.zero_copy = alias ? 1 : 0;
     return SBX_OK;
+}
+
+int sbx_render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* host_rgba) {
+    return render_host(ctx, p, shard, host_rgba, 0);
+}
+
+int sbx_render_host_rgba8(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, unsigned char* host_rgba8) {
+    return render_host(ctx, p, shard, host_rgba8, 1);
+}
+
+int sbx_render_device_rgba8(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, unsigned char* dev_rgba8, void* stream) {
+    if (((uintptr_t)dev_rgba8 & 3u) != 0) return ctx ? ctx->fail(SBX_ERR_INVALID, "rgba8 frame must be 4-byte aligned") : SBX_ERR_INVALID;
+    return render_launch(ctx, p, shard, (float*)dev_rgba8, stream, 0, 1);
 }
 
 int sbx_unshard_device(sbx_ctx* ctx, int width, int height, const sbx_shard* shard, const float* dev_part,
@@ -684,7 +699,7 @@ static int op_code(const char* op) {
         {"illum_cook_torrance", 55}, {"illum_blinn_phong", 56}, {"intersect_sphere", 57}, {"intersect_plane", 58},
         {"rotate_around_x", 64}, {"rotate_around_y", 65}, {"rotate_around_z", 66}, {"linear_to_srgb", 67}, {"band", 68},
         {"checkboard_pattern", 69}, {"remap", 70}, {"get_primary_ray", 71}, {"smoothstep", 72}, {"mod", 73},
-        {"fast_orthonormal_basis", 74}};
+        {"fast_orthonormal_basis", 74}, {"unorm8", 75}};
     for (const auto& e : table)
         if (!std::strcmp(e.name, op)) return e.code;
     return -1;

@@ -77,7 +77,7 @@ enum {
     OP_PHASE_HG = 48, OP_PHASE_RAYLEIGH, OP_PHASE_SCHLICK, OP_PHASE_ISO, OP_FRESNEL, OP_REFLECT, OP_REFRACT,
     OP_COOK_TORRANCE, OP_BLINN_PHONG, OP_INTERSECT_SPHERE, OP_INTERSECT_PLANE,
     OP_ROTATE_X = 64, OP_ROTATE_Y, OP_ROTATE_Z, OP_LINEAR_TO_SRGB, OP_BAND, OP_CHECKBOARD, OP_REMAP,
-    OP_PRIMARY_RAY, OP_SMOOTHSTEP, OP_MOD, OP_ORTHO_BASIS
+    OP_PRIMARY_RAY, OP_SMOOTHSTEP, OP_MOD, OP_ORTHO_BASIS, OP_UNORM8
 };
 
 // in: n rows of in_stride floats; out: n rows of out_stride floats (unused slots left untouched)
@@ -169,6 +169,7 @@ extern "C" __global__ void sbx_eval_op_kernel(const __grid_constant__ sbx_launch
         case OP_SMOOTHSTEP: o[0] = smoothstep(a[0], a[1], a[2]); break;
         case OP_MOD: o[0] = mod(a[0], a[1]); break;
         case OP_ORTHO_BASIS: { vec3 f, r; ops.fast_orthonormal_basis(V3(0), f, r); o[0] = f.x; o[1] = f.y; o[2] = f.z; o[3] = r.x; o[4] = r.y; o[5] = r.z; break; }
+        case OP_UNORM8: o[0] = (float)sbx_unorm8(a[0]); break;
         default: break;
     }
 #undef V3

@@ -49,6 +49,8 @@ def lib():
         L.sbx_shard_rows.argtypes = [P(Shard), C.c_int]
         L.sbx_render_device.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_void_p]
         L.sbx_render_host.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p]
+        L.sbx_render_host_rgba8.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p]
+        L.sbx_render_device_rgba8.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_void_p]
         L.sbx_render_frame.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_void_p]
         L.sbx_frame_alloc.argtypes = [C.c_void_p, C.c_size_t, P(C.c_void_p)]
         L.sbx_frame_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -69,6 +71,7 @@ EXPORTS = (
     "sbx_render_device", "sbx_render_host", "sbx_unshard_device", "sbx_set_option", "sbx_last_timing",
     "sbx_last_error", "sbx_strerror", "sbx_version", "sbx_eval_op", "sbx_render_frame", "sbx_frame_alloc",
     "sbx_frame_free", "sbx_frame_export", "sbx_frame_import", "sbx_frame_release", "sbx_frame_read",
+    "sbx_render_host_rgba8", "sbx_render_device_rgba8",
 )
 
 
@@ -131,6 +134,28 @@ class Renderer:
         self._check(self._L.sbx_render_host(self._ctx, C.byref(p), C.byref(sh), out.ctypes.data_as(C.c_void_p)),
                     "sbx_render_host")
         return out
+
+    def render_rgba8(self, width, height, u_time=0.0, shard=None, out=None, **uniforms):
+        """Render to host memory as R8G8B8A8_UNORM (the reference's 8-bit swap chain); returns uint8 [rows, width, 4]."""
+        p = uniforms.pop("params", None) or default_params(width, height, u_time, **uniforms)
+        sh = Shard(*shard) if shard is not None else Shard(1, 1, 0)
+        rows = len(shard_rows(sh.stripe_rows, sh.n_parts, sh.part, p.height))
+        if out is None:
+            out = np.empty((rows, p.width, 4), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.size == rows * p.width * 4 and out.flags["C_CONTIGUOUS"]
+        self._check(self._L.sbx_render_host_rgba8(self._ctx, C.byref(p), C.byref(sh), out.ctypes.data_as(C.c_void_p)),
+                    "sbx_render_host_rgba8")
+        return out
+
+    def render_rgba8_host_ptr(self, params, host_ptr, shard=None):
+        sh = Shard(*shard) if shard is not None else Shard(1, 1, 0)
+        self._check(self._L.sbx_render_host_rgba8(self._ctx, C.byref(params), C.byref(sh), C.c_void_p(host_ptr)),
+                    "sbx_render_host_rgba8")
+
+    def render_rgba8_into(self, params, dev_ptr, shard=None, stream=0):
+        sh = Shard(*shard) if shard is not None else Shard(1, 1, 0)
+        self._check(self._L.sbx_render_device_rgba8(self._ctx, C.byref(params), C.byref(sh), C.c_void_p(dev_ptr),
+                                                    C.c_void_p(stream)), "sbx_render_device_rgba8")
 
     def render_into(self, params, dev_ptr, shard=None, stream=0):
         """Render into device memory at `dev_ptr` (e.g. a torch tensor's data_ptr()) on `stream`."""

@@ -135,8 +135,9 @@ sbx_render(const __grid_constant__ sbx_launch L) {
     app.mainImage(c, sbx_glsl::vec2(float(x) + 0.5f, float(y) + 0.5f));
 
     if (stores) {
-        float4* dst = reinterpret_cast<float4*>(L.out) + (size_t)(L.out_is_frame ? y : lr) * (size_t)L.p.width + (size_t)x;
-        __stcs(dst, make_float4(c.x, c.y, c.z, c.w));
+        const size_t at = (size_t)(L.out_is_frame ? y : lr) * (size_t)L.p.width + (size_t)x;
+        if (L.out_rgba8) __stcs(reinterpret_cast<unsigned*>(L.out) + at, sbx_pack_unorm8(c.x, c.y, c.z, c.w));
+        else __stcs(reinterpret_cast<float4*>(L.out) + at, make_float4(c.x, c.y, c.z, c.w));
     }
 }
 

@@ -16,6 +16,16 @@
 
 #define SBX_FN __device__ __forceinline__
 
+// FLOAT -> UNORM8 of a D3D11 render target (the reference's 8-bit hosts, include/sbx.h): NaN -> 0, clamp to
+// [0, 1], * 255 + 0.5 in fp32, truncate.  fmaxf/fminf return the non-NaN operand, so NaN lands on 0.
+__device__ __forceinline__ unsigned sbx_unorm8(float v) {
+    return (unsigned)__float2int_rz(__fadd_rn(__fmul_rn(fminf(fmaxf(v, 0.0f), 1.0f), 255.0f), 0.5f));
+}
+__device__ __forceinline__ unsigned sbx_pack_unorm8(float r, float g, float b, float a) {
+    return sbx_unorm8(r) | (sbx_unorm8(g) << 8) | (sbx_unorm8(b) << 16) | (sbx_unorm8(a) << 24);
+}
+
+
 namespace sbx_glsl {
 
 struct vec2; struct vec3; struct vec4;

@@ -227,6 +227,51 @@ def test_host_frame_paths_agree(renderers):
     assert bits_equal(part.numpy(), pageable[abi.shard_rows(4, 3, 1, h)])
 
 
+def unorm8(frame):
+    """FLOAT -> R8G8B8A8_UNORM of the reference's swap chain (util/hlsltoy/src/hlsltoy.cpp:192): NaN -> 0, clamp,
+    * 255 + 0.5 in fp32, truncate."""
+    f = np.where(np.isnan(frame), np.float32(0), frame).astype(np.float32)
+    f = np.minimum(np.maximum(f, np.float32(0)), np.float32(1))
+    return (f * np.float32(255) + np.float32(0.5)).astype(np.float32).astype(np.int32).astype(np.uint8)
+
+
+@pytest.mark.parametrize("case", [c for c in FRAME_CASES if c[1] > 1], ids=frame_key)
+def test_rgba8_frames_match_quantised_reference_golden(case, golden_frames, renderers):
+    app, w, h, t, ov = case
+    want = unorm8(golden_frames[frame_key(case)])
+    for variant in ((None, "plugin") if app != "APP_SDF_AO" else ("plugin",)):
+        got = renderers(app, variant).render_rgba8(w, h, u_time=t, **ov)
+        assert got.dtype == np.uint8 and (got == want).all(), (variant, int((got != want).sum()))
+
+
+def test_rgba8_paths_shards_and_nan(renderers):
+    import torch
+
+    w, h, t = 333, 77, 2.0
+    r = renderers("APP_PLANET", None)
+    full = unorm8(r.render(w, h, u_time=t))
+    assert (r.render_rgba8(w, h, u_time=t) == full).all()
+    p = abi.default_params(w, h, t)
+    # device frame, pinned zero-copy frame, pageable frame, shard
+    dev = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda:0")
+    r.render_rgba8_into(p, dev.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (dev.cpu().numpy() == full).all()
+    pinned = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
+    r.render_rgba8_host_ptr(p, pinned.data_ptr())
+    assert r.timing()["zero_copy"] == 1 and (pinned.numpy() == full).all()
+    rows = abi.shard_rows(4, 3, 2, h)
+    assert (r.render_rgba8(w, h, u_time=t, shard=(4, 3, 2)) == full[rows]).all()
+    # the quantiser itself, incl. NaN / out-of-range / rounding ties, against the numpy statement
+    vals = np.array([np.nan, -1.0, -0.0, 0.0, 0.5 / 255, 1.5 / 255, 0.499999 / 255, 1.0, 1.0001, np.inf, -np.inf,
+                     0.7, 127.5 / 255, 254.5 / 255, 1e-30], np.float32)
+    assert unorm8(vals).tolist() == [0, 0, 0, 0, 1, 2, 0, 255, 255, 255, 0, 179, 128, 255, 0]
+    rng = np.random.default_rng(5)
+    more = np.concatenate([vals, rng.uniform(-0.1, 1.1, 100000).astype(np.float32), (np.arange(0, 511) / np.float32(510)).astype(np.float32)])
+    got = renderers("APP_EGG", "plugin").eval_op("unorm8", more, 1)[:, 0]
+    assert (got.astype(np.uint8) == unorm8(more)).all()
+
+
 def test_deterministic_run_to_run(renderers):
     r = renderers("APP_CLOUDS", None)
     a = r.render(320, 180, u_time=4.0)
