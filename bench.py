@@ -38,6 +38,8 @@ WORKLOADS = {
     "planet2160": ("APP_PLANET", 3840, 2160, 2.0, {}),
     "raytracer4320": ("APP_RAYTRACER", 7680, 4320, 1.0, {}),
     "egg256": ("APP_EGG", 256, 256, 1.0, {}),
+    "vinyl1080": ("APP_VINYL", 1920, 1080, 1.25, {}),
+    "sdf_ao1080": ("APP_SDF_AO", 1920, 1080, 0.5, {}),
 }
 METRIC = "Mpixels/sec at 1920x1080 (APP_CLOUDS)"
 # FP32 lane-instruction cost table for the algorithmic-work estimate (DESIGN.md "Roofline"):
@@ -224,7 +226,11 @@ def run_ours(args):
     rgba8 = args.format == "rgba8"
     if rgba8 and world > 1:
         raise SystemExit("bench.py: --format rgba8 is a 1-GPU measurement")
-    part = torch.empty((rows, w, 4), dtype=torch.uint8 if rgba8 else torch.float32, device=dev)
+    nf = max(1, args.frames)                                  # frames per step (time sequence in one launch)
+    if nf > 1 and (world > 1 or rgba8):
+        raise SystemExit("bench.py: --frames is a 1-GPU float-frame measurement")
+    seq_times = [t + k / 60.0 for k in range(nf)]             # a 60 Hz animation starting at the workload's u_time
+    part = torch.empty((nf * rows, w, 4), dtype=torch.uint8 if rgba8 else torch.float32, device=dev)
     px_bytes = 4 if rgba8 else 16
     frame = torch.empty((h, w, 4), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
     fused = world > 1 and args.gather == "p2p"
@@ -234,7 +240,9 @@ def run_ours(args):
 
     def step():
         """kernel (+ gather + unshard at N > 1), all on `stream`"""
-        if world == 1:
+        if nf > 1:
+            r.render_sequence_into(p, seq_times, part.data_ptr(), shard=shard, stream=stream.cuda_stream)
+        elif world == 1:
             (r.render_rgba8_into if rgba8 else r.render_into)(p, part.data_ptr(), shard=shard, stream=stream.cuda_stream)
         elif fused:
             shared.render(p, stripe)
@@ -297,11 +305,18 @@ def run_ours(args):
     if args.no_zero_copy:
         r.set_option("host_zero_copy", 0)
     if world == 1:
-        host = torch.empty((rows, w, 4), dtype=torch.uint8 if rgba8 else torch.float32).pin_memory()
+        host = torch.empty((nf * rows, w, 4), dtype=torch.uint8 if rgba8 else torch.float32).pin_memory()
+        import ctypes as _C
+        import numpy as _np
+        _times = _np.asarray(seq_times, dtype=_np.float32)
 
         def e2e_step():
-            (r.render_rgba8_host_ptr if rgba8 else r.render_host_ptr)(p, host.data_ptr(), shard=shard)   # sbx_render_host[_rgba8]: synchronous
-        d2h_bytes = int(px_bytes * rows * w)
+            if nf > 1:                                                # sbx_render_sequence_host: synchronous
+                r._check(r._L.sbx_render_sequence_host(r._ctx, _C.byref(p), _C.byref(sbx.Shard(*shard)), _times.ctypes.data_as(_C.c_void_p),
+                                                       nf, _C.c_void_p(host.data_ptr())), "sbx_render_sequence_host")
+            else:
+                (r.render_rgba8_host_ptr if rgba8 else r.render_host_ptr)(p, host.data_ptr(), shard=shard)   # sbx_render_host[_rgba8]
+        d2h_bytes = int(px_bytes * rows * w * nf)
     else:
         # N ranks: the frame is assembled on rank 0 (fused P2P stores or NCCL gather), then read back to the host there
         host = torch.empty((h, w, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
@@ -333,10 +348,10 @@ def run_ours(args):
 
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_src = peaks()
-        px = w * h
+        px = w * h * nf
         value = px * args.steps / (total_ms * 1e-3) * 1e-6
         avg_kernel_ms = total_kernel_ms / args.steps
-        alg_bytes = float(px_bytes) * rows * w            # this rank's launch: 16 (RGBA32F) or 4 (RGBA8) B/pixel written, 0 read
+        alg_bytes = float(px_bytes) * rows * w * nf       # this rank's launch: 16 (RGBA32F) or 4 (RGBA8) B/pixel written, 0 read
         achieved = alg_bytes / (avg_kernel_ms * 1e-3) * 1e-9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -346,7 +361,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s %dx%d u_time=%g %s" % (app, w, h, t, json.dumps(ov)), "variant": tm_variant(r, args), "format": "RGBA8_UNORM" if rgba8 else "RGBA32F",
+            "config": {"workload": "%s %dx%d u_time=%g %s" % (app, w, h, t, json.dumps(ov)), "variant": tm_variant(r, args), "format": "RGBA8_UNORM" if rgba8 else "RGBA32F", "frames_per_step": nf,
                        "l2": "flushed between steps (256 MiB memset on the same stream, outside the timed events); the frame is write-only",
                        "sharding": "none" if world == 1 else (
                            "%d-row stripes round-robin over %d ranks; every rank's render kernel stores its rows into rank 0's frame over NVLink "
@@ -401,7 +416,7 @@ def fp32_issue(workload, kernel_ms, sm_max_mhz, clocks):
     from shaderbox_b200.abi import Shard, default_params
 
     app, w, h, t, ov = WORKLOADS[workload]
-    if not (loader.have_oracle() and app != "APP_SDF_AO"):
+    if not (loader.have_oracle() and app not in ("APP_SDF_AO", "APP_VINYL")):
         return None
     parts = max(1, h // 16)
     rows = len(range(parts // 2, h, parts))
@@ -440,6 +455,7 @@ def main():
                     help="N>1: p2p = render kernels store into rank 0's frame over NVLink; nccl = compacted parts + ncclGather + unshard")
     ap.add_argument("--format", default="f32", choices=["f32", "rgba8"],
                     help="frame format: raw float4 (BASELINE.json) or the 8-bit swap-chain format of the reference's presenting hosts")
+    ap.add_argument("--frames", type=int, default=1, help="frames per step: a u_time sequence rendered by ONE launch (sbx_render_sequence_*)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: render in HBM and copy instead of storing into the host frame")

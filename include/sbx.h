@@ -145,6 +145,16 @@ int sbx_render_host_rgba8(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sh
 int sbx_render_frame(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
                      float* dev_frame, void* stream);
 
+/* A time sequence in ONE launch: frame k is rendered with u_time = times[k] (the animation loop of the
+ * reference's hosts -- `iGlobalTime` advancing per presented frame, src/uniform_buffer.h:34 -- batched, so
+ * small frames fill the GPU and the launch cost is paid once).  Output: n_frames consecutive frames (each
+ * rows*width float4, same row order / sharding as sbx_render_device).  Each frame is bit-identical to the
+ * one sbx_render_* produces for that u_time.  `times` is a HOST array of n_frames floats (1 <= n <= 65535). */
+int sbx_render_sequence_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
+                               const float* times, int n_frames, float* dev_rgba, void* stream);
+int sbx_render_sequence_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
+                             const float* times, int n_frames, float* host_rgba);
+
 /* Frame buffers that can be shared between the per-GPU processes of one box (CUDA IPC):
  * alloc on the owner, export a 64-byte handle, import it in a peer process (enables peer access). */
 #define SBX_IPC_HANDLE_BYTES 64

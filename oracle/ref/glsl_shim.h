@@ -210,4 +210,10 @@ inline mat2 operator*(const mat2& a, const mat2& b) {
     mat2 r; r.c[0] = a * b.c[0]; r.c[1] = a * b.c[1]; return r;
 }
 
+// GLSL builtins the vector library hands to a C++ build.  src/util_optics.h:16-36 supplies reflect/refract
+// itself (as members, which shadow these) for the apps that include it; src/app_vinyl.h:316 calls reflect
+// WITHOUT including util_optics.h, i.e. it relies on the host library's.  GLSL 4.x spec: I - 2*dot(N,I)*N,
+// the same expression as src/util_optics.h:20.
+inline vec3 reflect(const vec3& incident, const vec3& normal) { return incident - 2.0f * dot(normal, incident) * normal; }
+
 }  // namespace glsl

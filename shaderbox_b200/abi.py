@@ -13,7 +13,7 @@ SBX_ERR_COMPILE = -5
 SBX_ERR_NOMEM = -6
 SBX_ERR_UNSUPPORTED = -7
 
-APPS = ("APP_EGG", "APP_CLOUDS", "APP_ATMOSPHERE", "APP_PLANET", "APP_RAYTRACER")
+APPS = ("APP_EGG", "APP_CLOUDS", "APP_ATMOSPHERE", "APP_PLANET", "APP_RAYTRACER", "APP_SDF_AO", "APP_VINYL")
 
 
 class Params(C.Structure):

@@ -163,6 +163,8 @@ struct sbx_ctx {
     int opt_zero_copy = 1;        // sbx_render_host: store straight into pinned+mapped host frames
     int opt_coop_waves_x100 = 250;   // use the cooperative image when the grid is below this many waves of resident warps
 
+    CUdeviceptr times = 0;        // u_time values of a sequence launch
+    int times_cap = 0;
     CUdeviceptr frame = 0;        // internal frame for sbx_render_host
     size_t frame_bytes = 0;
     CUevent ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -384,6 +386,7 @@ void sbx_destroy(sbx_ctx* ctx) {
         if (ctx->util_module) ctx->cu->ModuleUnload(ctx->util_module);
         if (ctx->lut) ctx->cu->MemFree(ctx->lut);
         if (ctx->hash_tab) ctx->cu->MemFree(ctx->hash_tab);
+        if (ctx->times) ctx->cu->MemFree(ctx->times);
         if (ctx->frame) ctx->cu->MemFree(ctx->frame);
         if (ctx->ev0) ctx->cu->EventDestroy(ctx->ev0);
         if (ctx->ev1) ctx->cu->EventDestroy(ctx->ev1);
@@ -480,7 +483,7 @@ int sbx_set_option(sbx_ctx* ctx, const char* key, int value) {
 }
 
 static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_rgba, void* stream_,
-                         int out_is_frame, int out_rgba8 = 0) {
+                         int out_is_frame, int out_rgba8 = 0, const float* dev_times = nullptr, int n_frames = 1) {
     if (!ctx || !p || !dev_rgba || p->width <= 0 || p->height <= 0) return SBX_ERR_INVALID;
     if (!ctx->current) return ctx->fail(SBX_ERR_UNKNOWN_APP, "sbx_load_app was not called");
     sbx_shard s;
@@ -505,13 +508,14 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
         // single warps still marching; the cooperative image cuts every ray into P shorter pieces (multi-GPU).
         const long long warps = (long long)((p->width + img->tile_w - 1) / img->tile_w) * ((L.local_rows + img->tile_h - 1) / img->tile_h);
         const long long resident = (long long)ctx->sm_count * img->blocks_per_sm * img->warps_per_cta;
-        if (warps * 100 < resident * ctx->opt_coop_waves_x100) img = ctx->current_coop;
+        if (warps * n_frames * 100 < resident * ctx->opt_coop_waves_x100) img = ctx->current_coop;
     }
     L.tiles_x = (p->width + img->tile_w - 1) / img->tile_w;
     L.tiles_y = (L.local_rows + img->tile_h - 1) / img->tile_h;
     L.out = dev_rgba;
     L.out_is_frame = out_is_frame;
     L.out_rgba8 = out_rgba8;
+    L.times = dev_times;
     L.hash_tab = (const float4*)ctx->hash_tab;
     L.hash_bias = SBX_HASH_MAGIC_BITS + ctx->hash_lo;
     L.hash_len = ctx->hash_len;
@@ -522,7 +526,7 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
     const unsigned grid = (unsigned)((tiles + img->warps_per_cta - 1) / img->warps_per_cta);
     void* args[] = {&L};
     SBX_TRY(ctx->cu->EventRecord(ctx->ev0, stream), "cuEventRecord");
-    SBX_TRY(ctx->cu->LaunchKernel(img->render, grid, 1, 1, (unsigned)img->warps_per_cta * 32, 1, 1,
+    SBX_TRY(ctx->cu->LaunchKernel(img->render, grid, (unsigned)n_frames, 1, (unsigned)img->warps_per_cta * 32, 1, 1,
                                   SBX_LUT_MATH_BYTES, stream, args, nullptr),
             "launch sbx_render");
     SBX_TRY(ctx->cu->EventRecord(ctx->ev1, stream), "cuEventRecord");
@@ -552,6 +556,57 @@ static CUdeviceptr mapped_host_alias(sbx_ctx* ctx, const void* host) {
 
 int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_rgba, void* stream) {
     return render_launch(ctx, p, shard, dev_rgba, stream, 0);
+}
+
+int sbx_render_sequence_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, const float* times, int n_frames,
+                               float* dev_rgba, void* stream) {
+    if (!ctx || !times || n_frames < 1 || n_frames > 65535) return SBX_ERR_INVALID;
+    {
+        ctx_scope scope(ctx);
+        if (n_frames > ctx->times_cap) {
+            if (ctx->times) { ctx->cu->StreamSynchronize((CUstream)stream); ctx->cu->MemFree(ctx->times); }
+            ctx->times = 0;
+            ctx->times_cap = 0;
+            if (ctx->cu->MemAlloc(&ctx->times, (size_t)n_frames * sizeof(float)) != CUDA_SUCCESS)
+                return ctx->fail(SBX_ERR_NOMEM, "cuMemAlloc(times) failed");
+            ctx->times_cap = n_frames;
+        }
+        // stream-ordered after earlier launches that read the buffer; the host array is consumed before returning
+        SBX_TRY(ctx->cu->MemcpyHtoDAsync(ctx->times, times, (size_t)n_frames * sizeof(float), (CUstream)stream), "cuMemcpyHtoDAsync(times)");
+        SBX_TRY(ctx->cu->StreamSynchronize((CUstream)stream), "cuStreamSynchronize");
+    }
+    return render_launch(ctx, p, shard, dev_rgba, stream, 0, 0, (const float*)(uintptr_t)ctx->times, n_frames);
+}
+
+int sbx_render_sequence_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, const float* times, int n_frames,
+                             float* host_rgba) {
+    if (!ctx || !p || !host_rgba || !times || n_frames < 1 || p->width <= 0 || p->height <= 0) return SBX_ERR_INVALID;
+    sbx_shard s;
+    if (!valid_shard(shard, &s)) return ctx->fail(SBX_ERR_INVALID, "bad shard");
+    const size_t bytes = (size_t)n_frames * (size_t)shard_rows(s, p->height) * (size_t)p->width * 4 * sizeof(float);
+    if (bytes == 0) return SBX_OK;
+    CUdeviceptr alias = 0;
+    {
+        ctx_scope scope(ctx);
+        if (ctx->opt_zero_copy && ((uintptr_t)host_rgba & 15u) == 0) alias = mapped_host_alias(ctx, host_rgba);
+        if (!alias && bytes > ctx->frame_bytes) {
+            if (ctx->frame) ctx->cu->MemFree(ctx->frame);
+            ctx->frame = 0;
+            ctx->frame_bytes = 0;
+            if (ctx->cu->MemAlloc(&ctx->frame, bytes) != CUDA_SUCCESS) return ctx->fail(SBX_ERR_NOMEM, "cuMemAlloc(%zu) failed", bytes);
+            ctx->frame_bytes = bytes;
+        }
+    }
+    int st = sbx_render_sequence_device(ctx, p, &s, times, n_frames, (float*)(alias ? alias : ctx->frame), nullptr);
+    if (st != SBX_OK) return st;
+    ctx_scope scope(ctx);
+    if (!alias) SBX_TRY(ctx->cu->MemcpyDtoHAsync(host_rgba, ctx->frame, bytes, nullptr), "cuMemcpyDtoHAsync");
+    SBX_TRY(ctx->cu->EventRecord(ctx->ev2, nullptr), "cuEventRecord");
+    SBX_TRY(ctx->cu->StreamSynchronize(nullptr), "cuStreamSynchronize");
+    float ms = 0.0f;
+    if (ctx->cu->EventElapsedTime(&ms, ctx->ev1, ctx->ev2) == CUDA_SUCCESS) ctx->timing.d2h_ms = ms;
+    ctx->timing.zero_copy = alias ? 1 : 0;
+    return SBX_OK;
 }
 
 int sbx_render_frame(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_frame, void* stream) {

@@ -51,6 +51,8 @@ def lib():
         L.sbx_render_host.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p]
         L.sbx_render_host_rgba8.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p]
         L.sbx_render_device_rgba8.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_void_p]
+        L.sbx_render_sequence_device.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.sbx_render_sequence_host.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_int, C.c_void_p]
         L.sbx_render_frame.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_void_p]
         L.sbx_frame_alloc.argtypes = [C.c_void_p, C.c_size_t, P(C.c_void_p)]
         L.sbx_frame_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -71,7 +73,7 @@ EXPORTS = (
     "sbx_render_device", "sbx_render_host", "sbx_unshard_device", "sbx_set_option", "sbx_last_timing",
     "sbx_last_error", "sbx_strerror", "sbx_version", "sbx_eval_op", "sbx_render_frame", "sbx_frame_alloc",
     "sbx_frame_free", "sbx_frame_export", "sbx_frame_import", "sbx_frame_release", "sbx_frame_read",
-    "sbx_render_host_rgba8", "sbx_render_device_rgba8",
+    "sbx_render_host_rgba8", "sbx_render_device_rgba8", "sbx_render_sequence_device", "sbx_render_sequence_host",
 )
 
 
@@ -156,6 +158,23 @@ class Renderer:
         sh = Shard(*shard) if shard is not None else Shard(1, 1, 0)
         self._check(self._L.sbx_render_device_rgba8(self._ctx, C.byref(params), C.byref(sh), C.c_void_p(dev_ptr),
                                                     C.c_void_p(stream)), "sbx_render_device_rgba8")
+
+    def render_sequence(self, width, height, times, shard=None, **uniforms):
+        """Frames for u_time = times[k], all in one launch; returns float32 [len(times), rows, width, 4]."""
+        p = uniforms.pop("params", None) or default_params(width, height, 0.0, **uniforms)
+        sh = Shard(*shard) if shard is not None else Shard(1, 1, 0)
+        rows = len(shard_rows(sh.stripe_rows, sh.n_parts, sh.part, p.height))
+        t = np.ascontiguousarray(times, dtype=np.float32)
+        out = np.empty((len(t), rows, p.width, 4), dtype=np.float32)
+        self._check(self._L.sbx_render_sequence_host(self._ctx, C.byref(p), C.byref(sh), t.ctypes.data_as(C.c_void_p), len(t),
+                                                     out.ctypes.data_as(C.c_void_p)), "sbx_render_sequence_host")
+        return out
+
+    def render_sequence_into(self, params, times, dev_ptr, shard=None, stream=0):
+        sh = Shard(*shard) if shard is not None else Shard(1, 1, 0)
+        t = np.ascontiguousarray(times, dtype=np.float32)
+        self._check(self._L.sbx_render_sequence_device(self._ctx, C.byref(params), C.byref(sh), t.ctypes.data_as(C.c_void_p), len(t),
+                                                       C.c_void_p(dev_ptr), C.c_void_p(stream)), "sbx_render_sequence_device")
 
     def render_into(self, params, dev_ptr, shard=None, stream=0):
         """Render into device memory at `dev_ptr` (e.g. a torch tensor's data_ptr()) on `stream`."""

@@ -81,7 +81,7 @@ SBX_FN float sbx_uniform(const float& v) { return v; }
 SBX_FN int sbx_uniform(const int& v) { return v; }
 SBX_FN vec3 sbx_uniform(const float (&v)[3]) { return vec3(v[0], v[1], v[2]); }
 // read before uniform_buffer.h turns u_time / u_mouse into macros
-SBX_FN float sbx_param_time(const sbx_launch* L) { return L->p.u_time; }
+SBX_FN float sbx_param_time(const sbx_launch* L) { return L->times ? __ldg(L->times + blockIdx.y) : L->p.u_time; }
 SBX_FN vec4 sbx_param_mouse(const sbx_launch* L) {
     return vec4(L->p.u_mouse[0], L->p.u_mouse[1], L->p.u_mouse[2], L->p.u_mouse[3]);
 }
@@ -135,7 +135,7 @@ sbx_render(const __grid_constant__ sbx_launch L) {
     app.mainImage(c, sbx_glsl::vec2(float(x) + 0.5f, float(y) + 0.5f));
 
     if (stores) {
-        const size_t at = (size_t)(L.out_is_frame ? y : lr) * (size_t)L.p.width + (size_t)x;
+        const size_t at = ((size_t)blockIdx.y * (size_t)L.local_rows + (size_t)(L.out_is_frame ? y : lr)) * (size_t)L.p.width + (size_t)x;
         if (L.out_rgba8) __stcs(reinterpret_cast<unsigned*>(L.out) + at, sbx_pack_unorm8(c.x, c.y, c.z, c.w));
         else __stcs(reinterpret_cast<float4*>(L.out) + at, make_float4(c.x, c.y, c.z, c.w));
     }

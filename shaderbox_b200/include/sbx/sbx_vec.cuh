@@ -266,5 +266,9 @@ SBX_FN vec3 operator*(const vec3& v, const mat3& m) { return vec3(dot(v, m.c[0])
 SBX_FN mat3 operator*(const mat3& a, const mat3& b) { return mat3(a * b.c[0], a * b.c[1], a * b.c[2]); }
 SBX_FN mat2 operator*(const mat2& a, const mat2& b) { mat2 r; r.c[0] = a * b.c[0]; r.c[1] = a * b.c[1]; return r; }
 
+// GLSL reflect for app headers that do not include util_optics.h (src/app_vinyl.h:316); util_optics.h's own
+// member definition (src/util_optics.h:16-22) shadows this one where it is included.  Same expression.
+SBX_FN vec3 reflect(const vec3& incident, const vec3& normal) { return incident - 2.0f * dot(normal, incident) * normal; }
+
 }  // namespace sbx_glsl
 #endif  // SBX_VEC_CUH_

@@ -18,6 +18,8 @@ FRAME_CASES = [
     ("APP_RAYTRACER", 80, 45, 0.0, {}),
     ("APP_RAYTRACER", 80, 45, 1.0, {}),
     ("APP_SDF_AO", 80, 45, 0.5, {}),
+    ("APP_VINYL", 80, 45, 0.0, {}),
+    ("APP_VINYL", 96, 54, 1.25, {}),
     # ragged sizes: not a multiple of the 8x4 warp tile, 1-pixel rows/columns
     ("APP_EGG", 37, 19, 0.5, {}),
     ("APP_RAYTRACER", 1, 7, 0.0, {}),

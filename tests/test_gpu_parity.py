@@ -227,6 +227,19 @@ def test_host_frame_paths_agree(renderers):
     assert bits_equal(part.numpy(), pageable[abi.shard_rows(4, 3, 1, h)])
 
 
+@pytest.mark.parametrize("app,w,h", [("APP_EGG", 96, 64), ("APP_VINYL", 64, 36), ("APP_CLOUDS", 120, 67), ("APP_PLANET", 80, 45)])
+def test_time_sequence_in_one_launch_equals_single_frames(app, w, h, renderers):
+    times = [0.0, 0.25, 1.0, 1.5, 7.75]
+    r = renderers(app, None)
+    seq = r.render_sequence(w, h, times)
+    assert seq.shape == (len(times), h, w, 4)
+    for k, t in enumerate(times):
+        assert bits_equal(seq[k], r.render(w, h, u_time=t)), (app, t)
+    part = r.render_sequence(w, h, times[1:3], shard=(4, 3, 1))
+    for k, t in enumerate(times[1:3]):
+        assert bits_equal(part[k], r.render(w, h, u_time=t, shard=(4, 3, 1)))
+
+
 def unorm8(frame):
     """FLOAT -> R8G8B8A8_UNORM of the reference's swap chain (util/hlsltoy/src/hlsltoy.cpp:192): NaN -> 0, clamp,
     * 255 + 0.5 in fp32, truncate."""
