@@ -399,7 +399,15 @@ void sbx_destroy(sbx_ctx* ctx) {
 int sbx_compile_app(sbx_ctx* ctx, const char* app_header_path, const char* app_name, const char* image_out_path) {
     if (!app_header_path || !app_name) return SBX_ERR_INVALID;
     std::string cubin, log;
-    const int st = sbx::compile_app_header(app_header_path, app_name, {}, &cubin, &log);
+    // extra -D options for the image, e.g. SBX_COMPILE_DEFINES="SBX_MIN_CTAS_PER_SM=4;SBX_WARPS_PER_CTA=4" (launch shape
+    // of the pixel-loop kernel, sbx_kernel.cuh); the per-app defaults used by the build are in csrc/Makefile
+    std::vector<std::string> defines;
+    if (const char* env = std::getenv("SBX_COMPILE_DEFINES")) {
+        std::stringstream ss(env);
+        for (std::string d; std::getline(ss, d, ';');)
+            if (!d.empty()) defines.push_back(d);
+    }
+    const int st = sbx::compile_app_header(app_header_path, app_name, defines, &cubin, &log);
     if (st != SBX_OK) {
         if (ctx) ctx->last_error = log; else g_last_error = log;
         return st;
