@@ -388,6 +388,16 @@ def run_ours(args):
             cb = cpu_reference_rate(args.workload, budget_s=args.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["fp32_issue"] = fp32_issue(args.workload, avg_kernel_ms, sm_max_mhz, clocks)
+        if world == 1 and nf == 1 and not rgba8 and os.path.exists(tpath):
+            # the roof that binds: issue slots.  Warp instructions per launch are a property of (kernel image, workload),
+            # counted once by ncu (profiles/, smsp__inst_executed.sum); the time is this run's.
+            winst = json.load(open(tpath)).get(args.workload + "_warp_inst")
+            if winst and args.variant in (None, "native"):
+                clk = (clocks or {}).get("sm_mhz") or sm_max_mhz
+                slots = 148 * 4 * clk * 1e6 * avg_kernel_ms * 1e-3
+                line["issue_roofline"] = {"bound": "issue", "warp_inst_per_launch": winst, "achieved": winst / (avg_kernel_ms * 1e-3) * 1e-9,
+                                          "peak": 148 * 4 * clk * 1e-3, "unit": "G warp-inst/s", "frac": winst / slots,
+                                          "source": "ncu smsp__inst_executed.sum (profiles/traffic.json) / live kernel time; peak = 148 SMs x 4 schedulers x SM clock"}
         print(json.dumps(line), file=args.json_out, flush=True)
     if shared is not None:
         shared.close()
