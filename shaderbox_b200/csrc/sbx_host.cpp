@@ -531,6 +531,11 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
     L.lut = (const void*)ctx->lut;
 
     const long long tiles = (long long)L.tiles_x * L.tiles_y;
+    {   // the grid is rounded up to whole CTAs: the largest warp index is < tiles + warps_per_cta
+        const unsigned long long nmax = (unsigned long long)tiles + (unsigned long long)img->warps_per_cta;
+        L.tiles_x_magic = (nmax * (unsigned long long)L.tiles_x < (1ull << 40))
+                              ? ((1ull << 40) + (unsigned long long)L.tiles_x - 1) / (unsigned long long)L.tiles_x : 0ull;
+    }
     const unsigned grid = (unsigned)((tiles + img->warps_per_cta - 1) / img->warps_per_cta);
     void* args[] = {&L};
     SBX_TRY(ctx->cu->EventRecord(ctx->ev0, stream), "cuEventRecord");

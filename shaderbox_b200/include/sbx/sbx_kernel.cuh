@@ -49,29 +49,29 @@ __device__ __forceinline__ unsigned sbx_smem_addr(const void* p) {
 }
 __device__ __forceinline__ void sbx_stage_lut(const void* lut_global) {
     __shared__ __align__(8) unsigned long long sbx_lut_bar;
-    const unsigned bar = sbx_smem_addr(&sbx_lut_bar);
-    const unsigned dst = sbx_smem_addr(sbx_smem);
     if (threadIdx.x == 0) {
+        // one thread arms the barrier, issues the bulk copy and waits for its bytes to land; the others
+        // just park on the CTA barrier below (a spinning try_wait in every thread cost cheap apps 4 % of
+        // their issue slots -- profiles/r01g)
+        const unsigned bar = sbx_smem_addr(&sbx_lut_bar);
+        const unsigned dst = sbx_smem_addr(sbx_smem);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(SBX_LUT_MATH_BYTES) : "memory");
         asm volatile(
             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
             ::"r"(dst), "l"(lut_global), "n"(SBX_LUT_MATH_BYTES), "r"(bar) : "memory");
+        unsigned done = 0;
+        while (!done) {   // phase 0 completes when the 512 bytes have been written (acquire)
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n" : "=r"(done) : "r"(bar) : "memory");
+        }
     }
-    // every thread waits for phase 0 of the barrier
-    unsigned done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(bar) : "memory");
-    }
+    __syncthreads();   // orders the table (observed by thread 0) before every other thread's reads
 }
 
 namespace sbx_glsl {
@@ -110,8 +110,9 @@ sbx_render(const __grid_constant__ sbx_launch L) {
 
     const int warp = blockIdx.x * SBX_WARPS_PER_CTA + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    const int tile_x = warp % L.tiles_x;
-    const int tile_y = warp / L.tiles_x;
+    // warp -> (tile_x, tile_y): division by the host's magic number (exact for warp * tiles_x < 2^40, else 0 = divide)
+    const int tile_y = L.tiles_x_magic ? (int)(((unsigned long long)(unsigned)warp * L.tiles_x_magic) >> 40) : warp / L.tiles_x;
+    const int tile_x = warp - tile_y * L.tiles_x;
 #if SBX_LANES_PER_PIXEL == 1
     const int x = tile_x * SBX_TILE_W + (lane & (SBX_TILE_W - 1));
     const int lr = tile_y * SBX_TILE_H + (lane / SBX_TILE_W);
@@ -128,7 +129,7 @@ sbx_render(const __grid_constant__ sbx_launch L) {
 #endif
 
     // local (compacted) row -> frame row of this shard
-    const int y = ((lr / L.stripe_rows) * L.n_parts + L.part) * L.stripe_rows + lr % L.stripe_rows;
+    const int y = L.n_parts == 1 ? lr : ((lr / L.stripe_rows) * L.n_parts + L.part) * L.stripe_rows + lr % L.stripe_rows;
 
     sbx_glsl::sbx_app app(&L);
     sbx_glsl::vec4 c;

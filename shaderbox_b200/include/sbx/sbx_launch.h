@@ -26,6 +26,7 @@ typedef struct sbx_launch {
     int out_is_frame;           /* 0: out rows are this launch's local (compacted) rows; 1: out is the FULL frame
                                    (possibly a peer GPU's, mapped over NVLink) and rows land at their frame row */
     int out_rgba8;              /* 0: out is float4 RGBA32F per pixel; 1: out is one packed R8G8B8A8_UNORM word per pixel */
+    unsigned long long tiles_x_magic;   /* ceil(2^40 / tiles_x) when total_tiles * tiles_x < 2^40, else 0 (kernel divides) */
     const float* times;         /* NULL, or u_time of frame blockIdx.y of a sequence launch (device memory) */
     const void* lut;            /* SBX_LUT_MATH_BYTES of exp2/log2 tables in global memory (sbx_math.h) */
 } sbx_launch;
