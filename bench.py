@@ -318,19 +318,14 @@ def run_ours(args):
                 (r.render_rgba8_host_ptr if rgba8 else r.render_host_ptr)(p, host.data_ptr(), shard=shard)   # sbx_render_host[_rgba8]
         d2h_bytes = int(px_bytes * rows * w * nf)
     else:
-        # N ranks: the frame is assembled on rank 0 (fused P2P stores or NCCL gather), then read back to the host there
-        host = torch.empty((h, w, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+        # N ranks: every rank's kernel stores its stripes into ONE host frame shared by the processes (POSIX shared memory,
+        # pinned + mapped per GPU), each over its own PCIe link; complete after a stream-ordered all-reduce + sync
+        shost = multi.SharedHostFrame(r, w, h)
+        host = torch.from_numpy(shost.array) if rank == 0 else None
 
         def e2e_step():
-            if fused:
-                shared.render(p, stripe)
-                src = shared.tensor() if rank == 0 else None
-            else:
-                src = multi.render_distributed(r, p, stripe, frame_out=frame, part_out=part)
-            if rank == 0:
-                host.copy_(src, non_blocking=True)
-            torch.cuda.synchronize(dev)
-        d2h_bytes = int(16 * h * w)
+            shost.render(p, stripe)
+        d2h_bytes = int(16 * rows * w)
     for _ in range(2):
         e2e_step()
     barrier()
@@ -344,7 +339,7 @@ def run_ours(args):
         dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e_t[0])
     checksum = float(host[::97, ::89, :3].double().sum()) if host is not None else 0.0   # the host result is actually read
-    zero_copy = bool(r.timing()["zero_copy"]) if world == 1 else False
+    zero_copy = bool(r.timing()["zero_copy"]) if world == 1 else True   # N > 1: SharedHostFrame is mapped host memory by construction
 
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_src = peaks()
@@ -372,11 +367,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "sbx_render", "kernel_ms": avg_kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "write-only path: 16 B/pixel out, 0 in; the binding roof is FP32 issue (see fp32_issue)"},
+                         "note": "write-only path: 16 B/pixel out, 0 in; the binding roof is instruction issue (see issue_roofline)"},
             "e2e": {"value": px * args.steps / e2e_s * 1e-6, "unit": "Mpixels/s", "h2d_bytes_per_step": sbx_params_bytes(),
-                    "d2h_bytes_per_step": d2h_bytes, "checksum": checksum,
+                    "d2h_bytes_per_step": d2h_bytes if world == 1 else int(16 * w * h), "d2h_bytes_per_step_this_rank": d2h_bytes, "checksum": checksum,
                     "api": ("sbx_render_host (C ABI) via shaderbox_b200.Renderer.render_host_ptr, pinned host frame" if world == 1 else
-                            "sbx_render_frame on every rank into rank 0's frame + one device->host copy of the frame on rank 0"),
+                            "sbx_render_frame on every rank into one shared host frame (sbx_host_frame_register), all-reduce + stream sync"),
                     "d2h": "kernel stores straight into the pinned+mapped host frame (zero-copy over PCIe)" if zero_copy
                            else "frame assembled in HBM, then one async copy to pinned host memory"},
             "gpu_launches": launches_per_step * args.steps,
@@ -399,6 +394,8 @@ def run_ours(args):
                                           "peak": 148 * 4 * clk * 1e-3, "unit": "G warp-inst/s", "frac": winst / slots,
                                           "source": "ncu smsp__inst_executed.sum (profiles/traffic.json) / live kernel time; peak = 148 SMs x 4 schedulers x SM clock"}
         print(json.dumps(line), file=args.json_out, flush=True)
+    if world > 1:
+        shost.close()
     if shared is not None:
         shared.close()
     r.close()

@@ -163,6 +163,14 @@ int sbx_frame_free(sbx_ctx* ctx, float* dev);
 int sbx_frame_export(sbx_ctx* ctx, const float* dev, unsigned char handle[SBX_IPC_HANDLE_BYTES]);
 int sbx_frame_import(sbx_ctx* ctx, const unsigned char handle[SBX_IPC_HANDLE_BYTES], float** dev_out);
 int sbx_frame_release(sbx_ctx* ctx, float* imported);
+/* A HOST frame every GPU of the box can store into.  `host` is host memory the caller owns -- for one process
+ * per GPU, the same POSIX shared-memory mapping in every process.  Register pins and maps it for this
+ * context's device and returns the device-side alias; passing that alias to sbx_render_frame makes each
+ * rank's render kernel store its stripes straight into the shared host frame over ITS OWN PCIe link, so an
+ * N-GPU frame reaches host memory with no gather, no staging copy, and N links in parallel.  The frame is
+ * complete once every rank has synchronised its stream. */
+int sbx_host_frame_register(sbx_ctx* ctx, void* host, size_t bytes, float** dev_alias_out);
+int sbx_host_frame_unregister(sbx_ctx* ctx, void* host);
 /* Synchronous device->host read of a frame buffer (after ordering `stream`). */
 int sbx_frame_read(sbx_ctx* ctx, const float* dev, float* host, size_t bytes, void* stream);
 

@@ -60,6 +60,9 @@ struct driver_api {
     CUresult (*EventDestroy)(CUevent);
     CUresult (*GetErrorString)(CUresult, const char**);
     CUresult (*PointerGetAttribute)(void*, CUpointer_attribute, CUdeviceptr);
+    CUresult (*MemHostRegister)(void*, size_t, unsigned);
+    CUresult (*MemHostUnregister)(void*);
+    CUresult (*MemHostGetDevicePointer)(CUdeviceptr*, void*, unsigned);
     CUresult (*IpcGetMemHandle)(CUipcMemHandle*, CUdeviceptr);
     CUresult (*IpcOpenMemHandle)(CUdeviceptr*, CUipcMemHandle, unsigned);
     CUresult (*IpcCloseMemHandle)(CUdeviceptr);
@@ -110,6 +113,9 @@ driver_api* load_driver(std::string* err) {
     SBX_SYM(EventDestroy, "cuEventDestroy_v2")
     SBX_SYM(GetErrorString, "cuGetErrorString")
     SBX_SYM(PointerGetAttribute, "cuPointerGetAttribute")
+    SBX_SYM(MemHostRegister, "cuMemHostRegister_v2")
+    SBX_SYM(MemHostUnregister, "cuMemHostUnregister")
+    SBX_SYM(MemHostGetDevicePointer, "cuMemHostGetDevicePointer_v2")
     SBX_SYM(IpcGetMemHandle, "cuIpcGetMemHandle")
     SBX_SYM(IpcOpenMemHandle, "cuIpcOpenMemHandle_v2")
     SBX_SYM(IpcCloseMemHandle, "cuIpcCloseMemHandle")
@@ -667,6 +673,27 @@ int sbx_frame_release(sbx_ctx* ctx, float* imported) {
     if (!ctx || !imported) return SBX_ERR_INVALID;
     ctx_scope scope(ctx);
     SBX_TRY(ctx->cu->IpcCloseMemHandle((CUdeviceptr)(uintptr_t)imported), "cuIpcCloseMemHandle");
+    return SBX_OK;
+}
+
+int sbx_host_frame_register(sbx_ctx* ctx, void* host, size_t bytes, float** dev_alias_out) {
+    if (!ctx || !host || !dev_alias_out || bytes == 0) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    SBX_TRY(ctx->cu->MemHostRegister(host, bytes, CU_MEMHOSTREGISTER_PORTABLE | CU_MEMHOSTREGISTER_DEVICEMAP), "cuMemHostRegister");
+    CUdeviceptr d = 0;
+    const CUresult r = ctx->cu->MemHostGetDevicePointer(&d, host, 0);
+    if (r != CUDA_SUCCESS) {
+        ctx->cu->MemHostUnregister(host);
+        return ctx->check(r, "cuMemHostGetDevicePointer");
+    }
+    *dev_alias_out = (float*)(uintptr_t)d;
+    return SBX_OK;
+}
+
+int sbx_host_frame_unregister(sbx_ctx* ctx, void* host) {
+    if (!ctx || !host) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    SBX_TRY(ctx->cu->MemHostUnregister(host), "cuMemHostUnregister");
     return SBX_OK;
 }
 

@@ -59,6 +59,8 @@ def lib():
         L.sbx_frame_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
         L.sbx_frame_import.argtypes = [C.c_void_p, C.c_char_p, P(C.c_void_p)]
         L.sbx_frame_release.argtypes = [C.c_void_p, C.c_void_p]
+        L.sbx_host_frame_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_void_p)]
+        L.sbx_host_frame_unregister.argtypes = [C.c_void_p, C.c_void_p]
         L.sbx_frame_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.sbx_unshard_device.argtypes = [C.c_void_p, C.c_int, C.c_int, P(Shard), C.c_void_p, C.c_void_p, C.c_void_p]
         L.sbx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
@@ -74,6 +76,7 @@ EXPORTS = (
     "sbx_last_error", "sbx_strerror", "sbx_version", "sbx_eval_op", "sbx_render_frame", "sbx_frame_alloc",
     "sbx_frame_free", "sbx_frame_export", "sbx_frame_import", "sbx_frame_release", "sbx_frame_read",
     "sbx_render_host_rgba8", "sbx_render_device_rgba8", "sbx_render_sequence_device", "sbx_render_sequence_host",
+    "sbx_host_frame_register", "sbx_host_frame_unregister",
 )
 
 
@@ -208,6 +211,15 @@ class Renderer:
 
     def frame_release(self, ptr):
         self._check(self._L.sbx_frame_release(self._ctx, C.c_void_p(ptr)), "sbx_frame_release")
+
+    def host_frame_register(self, host_ptr, nbytes):
+        """Pin + map a (shared) host frame for this GPU; returns the device alias for render_frame."""
+        out = C.c_void_p()
+        self._check(self._L.sbx_host_frame_register(self._ctx, C.c_void_p(host_ptr), nbytes, C.byref(out)), "sbx_host_frame_register")
+        return out.value
+
+    def host_frame_unregister(self, host_ptr):
+        self._check(self._L.sbx_host_frame_unregister(self._ctx, C.c_void_p(host_ptr)), "sbx_host_frame_unregister")
 
     def frame_read(self, ptr, height, width, stream=0):
         out = np.empty((height, width, 4), dtype=np.float32)

@@ -142,3 +142,63 @@ class SharedFrame:
         else:
             self.renderer.frame_release(self.ptr)
         self.ptr = None
+
+
+class SharedHostFrame:
+    """The full frame in HOST memory shared by the per-GPU processes of one box (a POSIX shared-memory file mapped by
+    every rank, pinned and device-mapped by sbx_host_frame_register): each rank's render kernel stores its stripes
+    straight into it over its own PCIe link.  This is the end-to-end path of an N-GPU host: no gather to one GPU, no
+    device->host copy of the assembled frame; the frame is complete when every rank has synchronised its stream."""
+
+    def __init__(self, renderer, width, height, dst=0, group=None):
+        import mmap
+        import os
+
+        import numpy as np
+
+        self.renderer, self.width, self.height, self.dst, self.group = renderer, int(width), int(height), dst, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.nbytes = self.width * self.height * 16
+        size = (self.nbytes + mmap.PAGESIZE - 1) // mmap.PAGESIZE * mmap.PAGESIZE
+        name = [None]
+        if self.rank == dst:
+            name[0] = "/dev/shm/sbx_frame_%d_%d" % (os.getpid(), id(self) & 0xffff)
+            with open(name[0], "wb") as f:
+                f.truncate(size)
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=dst, group=group)
+        self.path = name[0]
+        self._file = open(self.path, "r+b")
+        self._map = mmap.mmap(self._file.fileno(), size)
+        self.array = np.frombuffer(self._map, dtype=np.float32, count=self.width * self.height * 4).reshape(self.height, self.width, 4)
+        self.host_ptr = self.array.ctypes.data
+        self.alias = renderer.host_frame_register(self.host_ptr, size)
+        dev = torch.device("cuda", renderer.device)
+        self._done = torch.zeros(1, dtype=torch.float32, device=dev)
+        if self.world > 1:
+            dist.barrier(group)
+        if self.rank == dst:
+            os.unlink(self.path)          # every rank holds its mapping; the name is no longer needed
+
+    def render(self, params, stripe_rows=DEFAULT_STRIPE_ROWS):
+        """One frame, synchronous: on return (every rank) the frame is complete in host memory (self.array)."""
+        assert params.width == self.width and params.height == self.height
+        dev = torch.device("cuda", self.renderer.device)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self.renderer.render_frame(params, self.alias, shard=shard_of(self.rank, self.world, stripe_rows), stream=stream)
+        if self.world > 1:
+            dist.all_reduce(self._done, group=self.group)   # stream-ordered after this rank's stores; completes when all ranks got here
+        torch.cuda.synchronize(dev)
+
+    def close(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(self.group)
+        self.renderer.host_frame_unregister(self.host_ptr)
+        self.array = None
+        try:
+            self._map.close()
+        except BufferError:
+            pass
+        self._file.close()

@@ -49,6 +49,15 @@ def _worker(rank, world, port, out_dir):
                 np.save(os.path.join(out_dir, "p2p%d.npy" % stripe), shared.tensor().cpu().numpy())
             dist.barrier()
         shared.close()
+        # path 3: every rank's kernel stores into ONE shared host frame over its own PCIe link
+        shost = multi.SharedHostFrame(r, W, H)
+        if rank == 0:
+            shost.array[:] = np.nan
+        dist.barrier()
+        shost.render(p, stripe_rows=4)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "host.npy"), np.array(shost.array))
+        shost.close()
         r.close()
     finally:
         dist.destroy_process_group()
@@ -67,5 +76,5 @@ def test_multi_gpu_frame_equals_single_gpu_frame(tmp_path, world):
     r = sbx.Renderer(APP, device=0)
     single = r.render(W, H, u_time=T, **OV)
     r.close()
-    for name in ("nccl.npy", "p2p4.npy", "p2p1.npy"):
+    for name in ("nccl.npy", "p2p4.npy", "p2p1.npy", "host.npy"):
         assert bits_equal(np.load(str(tmp_path / name)), single), name
