@@ -181,7 +181,8 @@ int sbx_unshard_device(sbx_ctx* ctx, int width, int height, const sbx_shard* sha
 
 /* Options: "use_hash_table" 0|1, "hash_table_log2" 9..22 (noise_iq memo table), "host_zero_copy" 0|1,
  * "coop_waves_x100" W (default 250): with the default variant, launches smaller than W/100 waves of resident warps
- * use the app's cooperative image (several lanes per pixel) if one is shipped; 0 = never. */
+ * use the app's 4-lanes-per-pixel cooperative image, launches smaller than 2W/100 waves the 2-lane one, if
+ * shipped; 0 = never. */
 int sbx_set_option(sbx_ctx* ctx, const char* key, int value);
 
 int sbx_last_timing(sbx_ctx* ctx, sbx_timing* out);

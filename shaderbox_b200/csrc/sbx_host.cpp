@@ -155,7 +155,8 @@ struct sbx_ctx {
 
     std::map<std::string, kernel_image> images;   // "APP_X/variant"
     kernel_image* current = nullptr;
-    kernel_image* current_coop = nullptr;   // cooperative image of the same app (P lanes per pixel), for small grids
+    kernel_image* current_coop = nullptr;   // cooperative images of the same app (4 and 2 lanes per pixel), for small grids
+    kernel_image* current_coop2 = nullptr;
     std::string current_app;
 
     CUmodule util_module = nullptr;
@@ -455,20 +456,20 @@ int sbx_load_app(sbx_ctx* ctx, const char* app_name, const char* variant) {
         }
         ctx->current = &it->second;
         ctx->current_coop = nullptr;
+        ctx->current_coop2 = nullptr;
         ctx->current_app = app_name;
         if (!(variant && *variant) && v == "native") {
-            // default selection only: the cooperative build of the same scene kernel, if shipped
-            const std::string ckey = std::string(app_name) + "/coop";
-            auto ct = ctx->images.find(ckey);
-            if (ct == ctx->images.end()) {
-                std::string cbin;
-                if (read_file(sbx::library_dir() + "/images/" + app_name + ".coop.cubin", &cbin) &&
-                    bind_image(ctx, ckey, cbin, "coop") == SBX_OK)
-                    ct = ctx->images.find(ckey);
-            }
-            if (ct != ctx->images.end()) {
-                ctx->current_coop = &ct->second;
-                ctx->current = &ctx->images.find(key)->second;
+            // default selection only: the cooperative builds of the same scene kernel, if shipped
+            for (const char* cv : {"coop", "coop2"}) {
+                const std::string ckey = std::string(app_name) + "/" + cv;
+                auto ct = ctx->images.find(ckey);
+                if (ct == ctx->images.end()) {
+                    std::string cbin;
+                    if (read_file(sbx::library_dir() + "/images/" + app_name + "." + cv + ".cubin", &cbin) &&
+                        bind_image(ctx, ckey, cbin, cv) == SBX_OK)
+                        ct = ctx->images.find(ckey);
+                }
+                if (ct != ctx->images.end()) (std::strcmp(cv, "coop") ? ctx->current_coop2 : ctx->current_coop) = &ct->second;
             }
         }
         return SBX_OK;
@@ -517,12 +518,14 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
     L.local_rows = shard_rows(s, p->height);
     if (L.local_rows == 0) return SBX_OK;
     kernel_image* img = ctx->current;
-    if (ctx->current_coop) {
-        // A frame (or one rank's share of it) that is only a couple of waves of resident warps ends in a long tail of
-        // single warps still marching; the cooperative image cuts every ray into P shorter pieces (multi-GPU).
-        const long long warps = (long long)((p->width + img->tile_w - 1) / img->tile_w) * ((L.local_rows + img->tile_h - 1) / img->tile_h);
+    if (ctx->current_coop || ctx->current_coop2) {
+        // A frame (or one rank's share of it) that is only a few waves of resident warps ends in a long tail of single
+        // warps still marching; the cooperative images cut every ray into P shorter pieces (multi-GPU).
+        // Measured on one rank's share of CLOUDS 1080p (tools/shard_time.py): 2.3 waves -> P=4 wins, 4.6 -> P=2, 9 -> P=1.
+        const long long warps = (long long)((p->width + img->tile_w - 1) / img->tile_w) * ((L.local_rows + img->tile_h - 1) / img->tile_h) * n_frames;
         const long long resident = (long long)ctx->sm_count * img->blocks_per_sm * img->warps_per_cta;
-        if (warps * n_frames * 100 < resident * ctx->opt_coop_waves_x100) img = ctx->current_coop;
+        if (ctx->current_coop && warps * 100 < resident * ctx->opt_coop_waves_x100) img = ctx->current_coop;
+        else if (ctx->current_coop2 && warps * 100 < resident * ctx->opt_coop_waves_x100 * 2) img = ctx->current_coop2;
     }
     L.tiles_x = (p->width + img->tile_w - 1) / img->tile_w;
     L.tiles_y = (L.local_rows + img->tile_h - 1) / img->tile_h;

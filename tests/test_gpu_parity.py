@@ -134,6 +134,9 @@ def test_default_variant_picks_the_cooperative_image_for_small_grids(renderers):
     part = r.render(1920, 1080, u_time=1.5, shard=(4, 8, 3))          # one rank's share at 8 GPUs: ~2 waves of warps
     assert r.timing()["lanes_per_pixel"] == 4
     assert bits_equal(part, big[abi.shard_rows(4, 8, 3, 1080)])
+    quarter = r.render(1920, 1080, u_time=1.5, shard=(4, 4, 1))      # at 4 GPUs: ~4.6 waves -> 2 lanes per pixel
+    assert r.timing()["lanes_per_pixel"] == 2
+    assert bits_equal(quarter, big[abi.shard_rows(4, 4, 1, 1080)])
     r.set_option("coop_waves_x100", 0)
     try:
         part1 = r.render(1920, 1080, u_time=1.5, shard=(4, 8, 3))
