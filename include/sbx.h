@@ -179,6 +179,16 @@ int sbx_frame_read(sbx_ctx* ctx, const float* dev, float* host, size_t bytes, vo
 int sbx_unshard_device(sbx_ctx* ctx, int width, int height, const sbx_shard* shard,
                        const float* dev_part, float* dev_frame, void* stream);
 
+/* The 3-D noise texture of the reference's USE_NOISE_TEX path (src/app_clouds.h:51-55), baked by
+ * util/ddsvolgen/src/ddsvolgen.cpp:52-61,101-116: a size^3 volume of R32G32B32A32_FLOAT voxels, x fastest, voxel
+ * (x,y,z) = (fbm_worley_tile((vec3(x,y,z) + .5) / size, 2., 1., .5), 0, 0, 0) with the 4-octave tiled Worley fbm
+ * of src/noise_worley.h + src/fbm.h:8.  Renders slices [z0, z0 + nz) into nz*size*size float4 (device or host).
+ * sbx_dds_volume_header fills the 148-byte DDS + DX10 header ddsvolgen writes in front of the data
+ * (ddsvolgen.cpp:69-92) for a size^3 RGBA32F volume; returns the number of bytes written (148) or < 0. */
+int sbx_bake_noise_volume_device(sbx_ctx* ctx, int size, int z0, int nz, float* dev_rgba, void* stream);
+int sbx_bake_noise_volume_host(sbx_ctx* ctx, int size, int z0, int nz, float* host_rgba);
+int sbx_dds_volume_header(int size, unsigned char* out, int capacity);
+
 /* Options: "use_hash_table" 0|1, "hash_table_log2" 9..22 (noise_iq memo table), "host_zero_copy" 0|1,
  * "coop_waves_x100" W (default 250): with the default variant, launches smaller than W/100 waves of resident warps
  * use the app's 4-lanes-per-pixel cooperative image, launches smaller than 2W/100 waves the 2-lane one, if

@@ -94,3 +94,28 @@ def ref_eval_op(op, inputs, out_width):
     if rc != 0:
         raise RuntimeError("sbxref_eval_op(%s) failed: %d" % (op, rc))
     return out
+
+
+def ref_bake_volume(size, z0=0, nz=None):
+    """Slices [z0, z0+nz) of the ddsvolgen noise volume from the reference's own noise_worley.h / fbm.h."""
+    nz = size - z0 if nz is None else nz
+    lib = _load(REF_SO)
+    out = np.empty((nz, size, size, 4), dtype=np.float32)
+    lib.sbxref_bake_volume.restype = C.c_int
+    lib.sbxref_bake_volume.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    rc = lib.sbxref_bake_volume(int(size), int(z0), int(nz), out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("sbxref_bake_volume failed: %d" % rc)
+    return out
+
+
+def ref_dds_header(size):
+    """The bytes ddsvolgen writes in front of the volume, built from the reference's vendored DDS.h."""
+    lib = _load(REF_SO)
+    buf = C.create_string_buffer(256)
+    lib.sbxref_dds_header.restype = C.c_int
+    lib.sbxref_dds_header.argtypes = [C.c_int, C.c_void_p, C.c_int]
+    n = lib.sbxref_dds_header(int(size), buf, 256)
+    if n <= 0:
+        raise RuntimeError("sbxref_dds_header failed: %d" % n)
+    return buf.raw[:n]

@@ -34,6 +34,12 @@ struct ops_t {
 #include "cornell_box.h"
     DECL_FBM_FUNC(fbm4, 4, noise_iq(p))
     DECL_FBM_FUNC_TILE(fbm_w3, 3, noise_w(p, L).x)
+    // util/ddsvolgen/src/ddsvolgen.cpp:52-61, verbatim
+    DECL_FBM_FUNC_TILE(fbm_worley_tile, 4, (1. - (noise_w(p, L).r + .25)))
+    float fbm_dds(vec3 &pos)
+    {
+        return fbm_worley_tile(pos, 2., 1., .5);
+    }
     ops_t() : iResolution(1.0f, 1.0f), iGlobalTime(0.0f), iMouse(0, 0, 0, 0) {}
 };
 #undef thread_local
@@ -128,3 +134,71 @@ extern "C" int sbxref_eval_op(const char* op, const float* in, int in_stride, fl
     }
     return SBX_OK;
 }
+
+
+// ---- util/ddsvolgen/src/ddsvolgen.cpp restated around the reference's own headers ------------------
+// The tool itself cannot be built here (VML + the Windows SDK); its per-voxel expression (:108-109) and
+// its header initialisation (:69-92) are reproduced with the reference's noise_worley.h / fbm.h (above)
+// and the reference's vendored DDS.h.
+#include <cstdint>
+typedef uint32_t DWORD;   // ddsvolgen.cpp:9 `typedef unsigned long DWORD` is 32 bits on its platform (Windows)
+#include "DDS.h"
+namespace ref_dds {
+using namespace DirectX;
+struct DDS {   // ddsvolgen.cpp:13-18
+    DWORD dwMagic;
+    DDS_HEADER header;
+    DDS_HEADER_DXT10 header10;
+};
+}
+
+extern "C" {
+
+// slices [z0, z0+nz) of the size^3 volume, RGBA32F, x fastest (ddsvolgen.cpp:101-116)
+int sbxref_bake_volume(int size, int z0, int nz, float* out) {
+    if (!out || size <= 0 || z0 < 0 || nz < 0 || z0 + nz > size) return SBX_ERR_INVALID;
+    using namespace ref_ops;
+    ops_t ops;
+    float* ptr = out;
+    for (size_t z = (size_t)z0; z < (size_t)(z0 + nz); z++)
+        for (size_t y = 0; y < (size_t)size; y++)
+            for (size_t x = 0; x < (size_t)size; x++) {
+                vec3 pos = (vec3(x, y, z) + .5f) / float(size);
+                *ptr++ = ops.fbm_dds(pos);
+                *ptr++ = 0.f;
+                *ptr++ = 0.f;
+                *ptr++ = 0.f;
+            }
+    return SBX_OK;
+}
+
+// the bytes ddsvolgen writes before the data (fwrite(&dds, sizeof(dds), 1, ...), :146) for a size^3 volume
+int sbxref_dds_header(int size_, unsigned char* out, int capacity) {
+    using namespace ref_dds;
+    const size_t size = (size_t)size_;
+    const size_t channels = 4;
+    using FLOAT = float;
+    DDS dds = { 0 };
+    dds.dwMagic = DDS_MAGIC;
+    dds.header.dwSize = sizeof(DDS_HEADER);
+    dds.header.dwFlags = DDS_HEADER_FLAGS_TEXTURE | DDS_HEADER_FLAGS_VOLUME | DDS_HEADER_FLAGS_PITCH;
+    dds.header.dwHeight = size;
+    dds.header.dwWidth = size;
+    dds.header.dwDepth = size;
+    dds.header.dwPitchOrLinearSize = (size * (sizeof(FLOAT) * channels) + 7) / 8;
+    dds.header.dwMipMapCount = 0;
+    dds.header.ddspf = DDSPF_DX10;
+    dds.header.dwCaps = DDS_SURFACE_FLAGS_TEXTURE | DDS_SURFACE_FLAGS_CUBEMAP;
+    dds.header.dwCaps2 = DDS_FLAGS_VOLUME;
+    DXGI_FORMAT fmt[] = { DXGI_FORMAT_R32_FLOAT, DXGI_FORMAT_R32G32_FLOAT, DXGI_FORMAT_R32G32B32_UINT, DXGI_FORMAT_R32G32B32A32_FLOAT };
+    dds.header10.dxgiFormat = fmt[channels - 1];
+    dds.header10.resourceDimension = DDS_DIMENSION_TEXTURE3D;
+    dds.header10.arraySize = 1;
+    dds.header10.miscFlag = 0;
+    dds.header10.miscFlags2 = 0;
+    if (!out || capacity < (int)sizeof(dds)) return SBX_ERR_INVALID;
+    std::memcpy(out, &dds, sizeof(dds));
+    return (int)sizeof(dds);
+}
+
+}  // extern "C"

@@ -4,4 +4,4 @@ Product code only: the C ABI (include/sbx.h, libsbx.so), its ctypes mirror and t
 images.  The CPU checkers live in oracle/ and are never imported from here.
 """
 from .abi import APPS, Params, Shard, Timing, default_params, shard_rows  # noqa: F401
-from .host import Renderer, SbxError, compile_app, lib, EXPORTS, LIB_PATH  # noqa: F401
+from .host import Renderer, SbxError, compile_app, dds_volume_header, lib, EXPORTS, LIB_PATH  # noqa: F401

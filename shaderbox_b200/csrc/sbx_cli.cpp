@@ -6,6 +6,7 @@
 //   sbx_cli render  <APP_NAME> <width> <height> <u_time> <out.rgba32f> [--variant native|plugin]
 //                   [--steps N] [--frames K] [--device D] [--ppm out.ppm] [--rgba8 out.rgba8]
 //   sbx_cli flatten <file.h>                                   (needs no GPU)
+//   sbx_cli bake <size> <out.dds> [--device D]                 (util/ddsvolgen: the 3-D noise texture, DDS + DX10 header + RGBA32F voxels)
 // `render` prints one JSON line with the kernel time of the last frame.  --ppm / --rgba8 render the
 // frame again through the 8-bit path (sbx_render_host_rgba8: what the reference's presenting hosts
 // show, util/hlsltoy/src/hlsltoy.cpp:192) and write it as a binary PPM (top row first) / raw bytes.
@@ -50,7 +51,8 @@ static int usage() {
             "usage: sbx_cli compile <app_header.h> <APP_NAME> <out.cubin>\n"
             "       sbx_cli render <APP_NAME> <width> <height> <u_time> <out.rgba32f|-> [--variant v] [--steps n] "
             "[--frames k] [--device d] [--ppm out.ppm] [--rgba8 out.rgba8]\n"
-            "       sbx_cli flatten <file.h>\n");
+            "       sbx_cli flatten <file.h>\n"
+            "       sbx_cli bake <size> <out.dds> [--device d]\n");
     return 2;
 }
 
@@ -70,6 +72,34 @@ int main(int argc, char** argv) {
         std::ifstream in(argv[2]);
         if (!in.good()) return 1;
         return flatten(in, std::cout);
+    }
+    if (!strcmp(argv[1], "bake")) {   // util/ddsvolgen/src/ddsvolgen.cpp:64-149 with the voxel loop on the GPU
+        if (argc < 4) return usage();
+        const int size = atoi(argv[2]);
+        int device = 0;
+        for (int i = 4; i + 1 < argc; i += 2) {
+            if (!strcmp(argv[i], "--device")) device = atoi(argv[i + 1]);
+            else return usage();
+        }
+        unsigned char header[148];
+        if (size <= 0 || sbx_dds_volume_header(size, header, sizeof header) != 148) return usage();
+        sbx_ctx* ctx = nullptr;
+        int st = sbx_create(device, &ctx);
+        if (st != SBX_OK) { fprintf(stderr, "sbx_create: %s: %s\n", sbx_strerror(st), sbx_last_error(nullptr)); return 1; }
+        std::vector<float> vol((size_t)size * size * size * 4);
+        st = sbx_bake_noise_volume_host(ctx, size, 0, size, vol.data());
+        if (st != SBX_OK) { fprintf(stderr, "sbx_bake_noise_volume_host: %s: %s\n", sbx_strerror(st), sbx_last_error(ctx)); return 1; }
+        sbx_timing tm{};
+        sbx_last_timing(ctx, &tm);
+        FILE* fp = fopen(argv[3], "wb");
+        if (!fp) { perror(argv[3]); return 2; }
+        fwrite(header, 1, sizeof header, fp);
+        fwrite(vol.data(), sizeof(float), vol.size(), fp);
+        fclose(fp);
+        printf("{\"baked\": \"%s\", \"size\": %d, \"kernel_ms\": %.3f, \"mvoxel_per_s\": %.1f}\n", argv[3], size, tm.kernel_ms,
+               tm.kernel_ms > 0 ? (double)size * size * size / tm.kernel_ms * 1e-3 : 0.0);
+        sbx_destroy(ctx);
+        return 0;
     }
     if (!strcmp(argv[1], "render")) {
         if (argc < 7) return usage();

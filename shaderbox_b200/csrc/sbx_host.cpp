@@ -160,7 +160,7 @@ struct sbx_ctx {
     std::string current_app;
 
     CUmodule util_module = nullptr;
-    CUfunction k_hash = nullptr, k_unshard = nullptr, k_eval = nullptr;
+    CUfunction k_hash = nullptr, k_unshard = nullptr, k_eval = nullptr, k_bake = nullptr;
 
     CUdeviceptr lut = 0;          // SBX_LUT_MATH_BYTES
     CUdeviceptr hash_tab = 0;     // 2 float4 per entry (noise_iq.h)
@@ -216,6 +216,7 @@ int load_util(sbx_ctx* ctx) {
     SBX_TRY(ctx->cu->ModuleGetFunction(&ctx->k_hash, ctx->util_module, "sbx_hash_table_kernel"), "get sbx_hash_table_kernel");
     SBX_TRY(ctx->cu->ModuleGetFunction(&ctx->k_unshard, ctx->util_module, "sbx_unshard_kernel"), "get sbx_unshard_kernel");
     SBX_TRY(ctx->cu->ModuleGetFunction(&ctx->k_eval, ctx->util_module, "sbx_eval_op_kernel"), "get sbx_eval_op_kernel");
+    SBX_TRY(ctx->cu->ModuleGetFunction(&ctx->k_bake, ctx->util_module, "sbx_bake_volume_kernel"), "get sbx_bake_volume_kernel");
     return SBX_OK;
 }
 
@@ -771,6 +772,78 @@ int sbx_unshard_device(sbx_ctx* ctx, int width, int height, const sbx_shard* sha
                                   (CUstream)stream_, args, nullptr),
             "launch sbx_unshard_kernel");
     return SBX_OK;
+}
+
+int sbx_bake_noise_volume_device(sbx_ctx* ctx, int size, int z0, int nz, float* dev_rgba, void* stream_) {
+    if (!ctx || !dev_rgba || size <= 0 || size > 2048 || z0 < 0 || nz < 0 || z0 + nz > size) return SBX_ERR_INVALID;
+    if (nz == 0) return SBX_OK;
+    CUstream stream = (CUstream)stream_;
+    ctx_scope scope(ctx);
+    int st = ensure_tables(ctx, stream);
+    if (st != SBX_OK) return st;
+    sbx_launch L;
+    std::memset(&L, 0, sizeof L);
+    L.lut = (const void*)ctx->lut;
+    const long long total = (long long)size * size * nz;
+    void* args[] = {&L, &dev_rgba, &size, &z0, &nz};
+    SBX_TRY(ctx->cu->EventRecord(ctx->ev0, stream), "cuEventRecord");
+    SBX_TRY(ctx->cu->LaunchKernel(ctx->k_bake, (unsigned)((total + 127) / 128), 1, 1, 128, 1, 1, SBX_LUT_MATH_BYTES, stream, args, nullptr),
+            "launch sbx_bake_volume_kernel");
+    SBX_TRY(ctx->cu->EventRecord(ctx->ev1, stream), "cuEventRecord");
+    ctx->timing.launches = 1;
+    ctx->timing.grid_blocks = (int)((total + 127) / 128);
+    ctx->timing.block_threads = 128;
+    ctx->timing.kernel_ms = -1.0f;
+    return SBX_OK;
+}
+
+int sbx_bake_noise_volume_host(sbx_ctx* ctx, int size, int z0, int nz, float* host_rgba) {
+    if (!ctx || !host_rgba || size <= 0 || nz < 0) return SBX_ERR_INVALID;
+    const size_t bytes = (size_t)size * size * (size_t)nz * 4 * sizeof(float);
+    if (bytes == 0) return SBX_OK;
+    {
+        ctx_scope scope(ctx);
+        if (bytes > ctx->frame_bytes) {
+            if (ctx->frame) ctx->cu->MemFree(ctx->frame);
+            ctx->frame = 0;
+            ctx->frame_bytes = 0;
+            if (ctx->cu->MemAlloc(&ctx->frame, bytes) != CUDA_SUCCESS) return ctx->fail(SBX_ERR_NOMEM, "cuMemAlloc(%zu) failed", bytes);
+            ctx->frame_bytes = bytes;
+        }
+    }
+    int st = sbx_bake_noise_volume_device(ctx, size, z0, nz, (float*)(uintptr_t)ctx->frame, nullptr);
+    if (st != SBX_OK) return st;
+    ctx_scope scope(ctx);
+    SBX_TRY(ctx->cu->MemcpyDtoHAsync(host_rgba, ctx->frame, bytes, nullptr), "cuMemcpyDtoHAsync");
+    SBX_TRY(ctx->cu->StreamSynchronize(nullptr), "cuStreamSynchronize");
+    return SBX_OK;
+}
+
+// util/ddsvolgen/src/ddsvolgen.cpp:13-18,69-92 -- struct DDS { DWORD magic; DDS_HEADER; DDS_HEADER_DXT10 } with the
+// constants of DirectXTex's DDS.h (lib/DirectXTex/DirectXTex/DDS.h:40,156-192; published DDS file format) and the
+// field values ddsvolgen sets, quirks included (dwCaps carries the "cubemap" bit, pitch is (size*16 + 7) / 8).
+int sbx_dds_volume_header(int size, unsigned char* out, int capacity) {
+    if (!out || size <= 0 || capacity < 148) return SBX_ERR_INVALID;
+    uint32_t w[37];
+    std::memset(w, 0, sizeof w);
+    w[0] = 0x20534444u;                                  // DDS_MAGIC "DDS "
+    w[1] = 124u;                                         // header.dwSize = sizeof(DDS_HEADER)
+    w[2] = 0x00001007u | 0x00800000u | 0x00000008u;      // DDS_HEADER_FLAGS_TEXTURE | _VOLUME | _PITCH
+    w[3] = (uint32_t)size;                               // dwHeight
+    w[4] = (uint32_t)size;                               // dwWidth
+    w[5] = (uint32_t)(((size_t)size * 16 + 7) / 8);      // dwPitchOrLinearSize
+    w[6] = (uint32_t)size;                               // dwDepth
+    w[7] = 0u;                                           // dwMipMapCount; w[8..18] dwReserved1[11]
+    w[19] = 32u; w[20] = 0x00000004u; w[21] = 0x30315844u;   // ddspf = DDSPF_DX10: size, DDS_FOURCC, 'DX10', zeros
+    w[27] = 0x00001000u | 0x00000008u;                   // dwCaps = DDS_SURFACE_FLAGS_TEXTURE | DDS_SURFACE_FLAGS_CUBEMAP
+    w[28] = 0x00200000u;                                 // dwCaps2 = DDS_FLAGS_VOLUME; w[29..31] dwCaps3, dwCaps4, dwReserved2
+    w[32] = 2u;                                          // header10.dxgiFormat = DXGI_FORMAT_R32G32B32A32_FLOAT
+    w[33] = 4u;                                          // resourceDimension = DDS_DIMENSION_TEXTURE3D
+    w[34] = 0u;                                          // miscFlag
+    w[35] = 1u;                                          // arraySize
+    w[36] = 0u;                                          // miscFlags2
+    std::memcpy(out, w, 148);
+    return 148;
 }
 
 int sbx_last_timing(sbx_ctx* ctx, sbx_timing* out) {

@@ -65,9 +65,28 @@ struct sbx_ops {
 #include "cornell_box.h"
     DECL_FBM_FUNC(fbm4, 4, noise_iq(p))
     DECL_FBM_FUNC_TILE(fbm_w3, 3, noise_w(p, L).x)
+    // util/ddsvolgen/src/ddsvolgen.cpp:52-61: the tiled-Worley fbm baked into the 3-D noise texture
+    DECL_FBM_FUNC_TILE(fbm_worley_tile, 4, (1.0f - (noise_w(p, L).r + .25f)))
+    SBX_FN float fbm_dds(_in(vec3) pos) { return fbm_worley_tile(pos, 2.0f, 1.0f, .5f); }
     __device__ explicit sbx_ops(const sbx_launch* L) : sbx_L(L), iResolution(1.0f, 1.0f), iGlobalTime(0.0f) {}
 };
 }  // namespace sbx_glsl
+
+// The 3-D noise texture bake of util/ddsvolgen/src/ddsvolgen.cpp:101-116 (the USE_NOISE_TEX input of
+// src/app_clouds.h:51-55): voxel (x, y, z) of a size^3 R32G32B32A32_FLOAT volume, x fastest, holds
+// (fbm_dds((vec3(x, y, z) + .5) / size), 0, 0, 0).  One thread per voxel, one float4 store each: the
+// reference's four host threads over z-slabs become one grid.  ~330 sines per voxel -- compute bound.
+extern "C" __global__ void __launch_bounds__(128)
+sbx_bake_volume_kernel(const __grid_constant__ sbx_launch L, float4* __restrict__ out, int size, int z0, int nz) {
+    using namespace sbx_glsl;
+    sbx_util_stage_lut(L.lut);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)size * size * nz) return;
+    const int x = (int)(i % size), y = (int)((i / size) % size), z = z0 + (int)(i / ((long long)size * size));
+    sbx_ops ops(&L);
+    const vec3 pos = (vec3(float(x), float(y), float(z)) + .5f) / float(size);
+    __stcs(out + i, make_float4(ops.fbm_dds(pos), 0.0f, 0.0f, 0.0f));
+}
 
 enum {
     OP_SINF = 0, OP_COSF, OP_TANF, OP_EXPF, OP_POWF, OP_ACOSF, OP_ATAN2F, OP_SQRTF, OP_DIVF,

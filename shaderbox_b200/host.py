@@ -61,6 +61,9 @@ def lib():
         L.sbx_frame_release.argtypes = [C.c_void_p, C.c_void_p]
         L.sbx_host_frame_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_void_p)]
         L.sbx_host_frame_unregister.argtypes = [C.c_void_p, C.c_void_p]
+        L.sbx_bake_noise_volume_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.sbx_bake_noise_volume_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.sbx_dds_volume_header.argtypes = [C.c_int, C.c_void_p, C.c_int]
         L.sbx_frame_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.sbx_unshard_device.argtypes = [C.c_void_p, C.c_int, C.c_int, P(Shard), C.c_void_p, C.c_void_p, C.c_void_p]
         L.sbx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
@@ -77,7 +80,17 @@ EXPORTS = (
     "sbx_frame_free", "sbx_frame_export", "sbx_frame_import", "sbx_frame_release", "sbx_frame_read",
     "sbx_render_host_rgba8", "sbx_render_device_rgba8", "sbx_render_sequence_device", "sbx_render_sequence_host",
     "sbx_host_frame_register", "sbx_host_frame_unregister",
+    "sbx_bake_noise_volume_device", "sbx_bake_noise_volume_host", "sbx_dds_volume_header",
 )
+
+
+def dds_volume_header(size):
+    """The 148-byte DDS + DX10 header ddsvolgen writes in front of a size^3 RGBA32F volume (needs no GPU)."""
+    buf = C.create_string_buffer(148)
+    n = lib().sbx_dds_volume_header(int(size), buf, 148)
+    if n != 148:
+        raise SbxError(n, "sbx_dds_volume_header")
+    return buf.raw
 
 
 def compile_app(header_path, app_name, image_out_path):
@@ -220,6 +233,19 @@ class Renderer:
 
     def host_frame_unregister(self, host_ptr):
         self._check(self._L.sbx_host_frame_unregister(self._ctx, C.c_void_p(host_ptr)), "sbx_host_frame_unregister")
+
+    def bake_noise_volume(self, size, z0=0, nz=None):
+        """Slices [z0, z0+nz) of the ddsvolgen noise volume; returns float32 [nz, size, size, 4]."""
+        nz = size - z0 if nz is None else nz
+        out = np.empty((nz, size, size, 4), dtype=np.float32)
+        self._check(self._L.sbx_bake_noise_volume_host(self._ctx, int(size), int(z0), int(nz), out.ctypes.data_as(C.c_void_p)),
+                    "sbx_bake_noise_volume_host")
+        return out
+
+    def bake_noise_volume_into(self, size, dev_ptr, z0=0, nz=None, stream=0):
+        nz = size - z0 if nz is None else nz
+        self._check(self._L.sbx_bake_noise_volume_device(self._ctx, int(size), int(z0), int(nz), C.c_void_p(dev_ptr), C.c_void_p(stream)),
+                    "sbx_bake_noise_volume_device")
 
     def frame_read(self, ptr, height, width, stream=0):
         out = np.empty((height, width, 4), dtype=np.float32)

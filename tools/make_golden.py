@@ -6,6 +6,7 @@ the fixtures travel to the GPU box, the reference does not.
 
 frames.npz : per case  <key>/rgba float32 [h, w, 4], plus the uniforms in the key
 ops.npz    : per operator <op>/in, <op>/out (sbx_eval_op layouts, tests/opcases.py inputs)
+volume.npz : the util/ddsvolgen noise volume (16^3 whole, two 128^3 slices) and its DDS header bytes
 """
 import os
 import sys
@@ -38,7 +39,11 @@ def main():
         ops[op + "/in"] = a
         ops[op + "/out"] = loader.ref_eval_op(op, a, ow)
     np.savez_compressed(os.path.join(OUT, "ops.npz"), **ops)
-    for f in ("frames.npz", "ops.npz"):
+    # the ddsvolgen noise volume: a whole 16^3 bake, two slices of the shipped 128^3 size, and the DDS header bytes
+    vol = {"v16": loader.ref_bake_volume(16), "v128_z0": loader.ref_bake_volume(128, 0, 1), "v128_z77": loader.ref_bake_volume(128, 77, 1),
+           "hdr128": np.frombuffer(loader.ref_dds_header(128), dtype=np.uint8), "hdr16": np.frombuffer(loader.ref_dds_header(16), dtype=np.uint8)}
+    np.savez_compressed(os.path.join(OUT, "volume.npz"), **vol)
+    for f in ("frames.npz", "ops.npz", "volume.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 
