@@ -319,7 +319,7 @@ def run_ours(args):
         d2h_bytes = int(px_bytes * rows * w * nf)
     else:
         # N ranks: every rank's kernel stores its stripes into ONE host frame shared by the processes (POSIX shared memory,
-        # pinned + mapped per GPU), each over its own PCIe link; complete after a stream-ordered all-reduce + sync
+        # pinned + mapped per GPU), each over its own PCIe link; complete after each rank's stream sync + a host barrier
         shost = multi.SharedHostFrame(r, w, h)
         host = torch.from_numpy(shost.array) if rank == 0 else None
 
@@ -371,7 +371,7 @@ def run_ours(args):
             "e2e": {"value": px * args.steps / e2e_s * 1e-6, "unit": "Mpixels/s", "h2d_bytes_per_step": sbx_params_bytes(),
                     "d2h_bytes_per_step": d2h_bytes if world == 1 else int(16 * w * h), "d2h_bytes_per_step_this_rank": d2h_bytes, "checksum": checksum,
                     "api": ("sbx_render_host (C ABI) via shaderbox_b200.Renderer.render_host_ptr, pinned host frame" if world == 1 else
-                            "sbx_render_frame on every rank into one shared host frame (sbx_host_frame_register), all-reduce + stream sync"),
+                            "sbx_render_frame on every rank into one shared host frame (sbx_host_frame_register); stream sync, then a host barrier on a shared control page"),
                     "d2h": "kernel stores straight into the pinned+mapped host frame (zero-copy over PCIe)" if zero_copy
                            else "frame assembled in HBM, then one async copy to pinned host memory"},
             "gpu_launches": launches_per_step * args.steps,

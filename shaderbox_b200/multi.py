@@ -148,7 +148,12 @@ class SharedHostFrame:
     """The full frame in HOST memory shared by the per-GPU processes of one box (a POSIX shared-memory file mapped by
     every rank, pinned and device-mapped by sbx_host_frame_register): each rank's render kernel stores its stripes
     straight into it over its own PCIe link.  This is the end-to-end path of an N-GPU host: no gather to one GPU, no
-    device->host copy of the assembled frame; the frame is complete when every rank has synchronised its stream."""
+    device->host copy of the assembled frame.
+
+    Completion is a HOST-side barrier, in this order: every rank synchronises its own stream (its stores have then
+    landed in host memory), publishes the frame number in its slot of a control page behind the frame, and waits
+    until every slot shows it.  (A GPU-side collective after the kernel would not do: nothing orders one GPU's
+    PCIe writes to host memory before its NVLink traffic to another GPU.)"""
 
     def __init__(self, renderer, width, height, dst=0, group=None):
         import mmap
@@ -160,10 +165,19 @@ class SharedHostFrame:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.nbytes = self.width * self.height * 16
-        size = (self.nbytes + mmap.PAGESIZE - 1) // mmap.PAGESIZE * mmap.PAGESIZE
+        page = mmap.PAGESIZE
+        frame_bytes = (self.nbytes + page - 1) // page * page
+        size = frame_bytes + page                               # + one control page: int64 slot per rank
         name = [None]
         if self.rank == dst:
-            name[0] = "/dev/shm/sbx_frame_%d_%d" % (os.getpid(), id(self) & 0xffff)
+            base = "/dev/shm"
+            try:
+                st = os.statvfs(base)
+                if st.f_bavail * st.f_frsize < size + (16 << 20):
+                    base = "/tmp"                               # a small /dev/shm (container default 64 MB): any file works
+            except OSError:
+                base = "/tmp"
+            name[0] = "%s/sbx_frame_%d_%d" % (base, os.getpid(), id(self) & 0xffff)
             with open(name[0], "wb") as f:
                 f.truncate(size)
         if self.world > 1:
@@ -172,10 +186,10 @@ class SharedHostFrame:
         self._file = open(self.path, "r+b")
         self._map = mmap.mmap(self._file.fileno(), size)
         self.array = np.frombuffer(self._map, dtype=np.float32, count=self.width * self.height * 4).reshape(self.height, self.width, 4)
+        self._slots = np.frombuffer(self._map, dtype=np.int64, count=self.world, offset=frame_bytes)
+        self._epoch = 0
         self.host_ptr = self.array.ctypes.data
-        self.alias = renderer.host_frame_register(self.host_ptr, size)
-        dev = torch.device("cuda", renderer.device)
-        self._done = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.alias = renderer.host_frame_register(self.host_ptr, frame_bytes)
         if self.world > 1:
             dist.barrier(group)
         if self.rank == dst:
@@ -185,11 +199,14 @@ class SharedHostFrame:
         """One frame, synchronous: on return (every rank) the frame is complete in host memory (self.array)."""
         assert params.width == self.width and params.height == self.height
         dev = torch.device("cuda", self.renderer.device)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        self.renderer.render_frame(params, self.alias, shard=shard_of(self.rank, self.world, stripe_rows), stream=stream)
-        if self.world > 1:
-            dist.all_reduce(self._done, group=self.group)   # stream-ordered after this rank's stores; completes when all ranks got here
-        torch.cuda.synchronize(dev)
+        stream = torch.cuda.current_stream(dev)
+        self.renderer.render_frame(params, self.alias, shard=shard_of(self.rank, self.world, stripe_rows), stream=stream.cuda_stream)
+        stream.synchronize()                                    # this rank's stripes are in host memory
+        self._epoch += 1
+        self._slots[self.rank] = self._epoch
+        slots, epoch = self._slots, self._epoch
+        while int(slots.min()) < epoch:                         # host barrier on the control page
+            pass
 
     def close(self):
         torch.cuda.synchronize()
@@ -197,6 +214,7 @@ class SharedHostFrame:
             dist.barrier(self.group)
         self.renderer.host_frame_unregister(self.host_ptr)
         self.array = None
+        self._slots = None
         try:
             self._map.close()
         except BufferError:
