@@ -20,12 +20,14 @@
 
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
 #define SBX_MATH_FN __device__ __forceinline__
+#define SBX_MATH_COLD static __device__ __noinline__   /* rare paths: one copy per kernel, not one per call site */
 #define SBX_DEVICE_CODE 1
 #else
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
 #define SBX_MATH_FN static inline
+#define SBX_MATH_COLD static inline
 #endif
 
 #if defined(SBX_DEVICE_CODE)
@@ -163,7 +165,8 @@ SBX_MATH_FN double sbx_reduce_fast(double x, int* np) {
 }
 
 // |x| >= 120: 96 bits of 4/pi times the 24-bit mantissa, keep the top 2 bits as the quadrant
-SBX_MATH_FN double sbx_reduce_large(sbx_u32 xi, int* np) {
+typedef struct sbx_reduced { double x; int n; } sbx_reduced;   // returned by value: the out-of-line copy then needs no stack slot in its callers
+SBX_MATH_COLD sbx_reduced sbx_reduce_large_cold(sbx_u32 xi) {
     const int base = (int)((xi >> 26) & 15u);
     const int shift = (int)((xi >> 23) & 7u);
     sbx_u64 n, res0, res1, res2;
@@ -176,8 +179,15 @@ SBX_MATH_FN double sbx_reduce_large(sbx_u32 xi, int* np) {
     res0 += res1;
     n = (res0 + (1ull << 61)) >> 62;
     res0 -= n << 62;
-    *np = (int)n;
-    return (double)(sbx_i64)res0 * 0x1.921fb54442d18p-62;
+    sbx_reduced r;
+    r.n = (int)n;
+    r.x = (double)(sbx_i64)res0 * 0x1.921fb54442d18p-62;
+    return r;
+}
+SBX_MATH_FN double sbx_reduce_large(sbx_u32 xi, int* np) {
+    const sbx_reduced r = sbx_reduce_large_cold(xi);
+    *np = r.n;
+    return r.x;
 }
 
 SBX_MATH_FN float sbx_sinf(float y) {

@@ -178,14 +178,22 @@ SBX_FN float2 pk_mix(float2 x, float2 y, float one_minus_a, float a) { return pk
 SBX_FN float2 pk_mix(float2 x, float2 y, float2 one_minus_a, float2 a) { return pk_add(pk_mul(x, one_minus_a), pk_mul(y, a)); }
 
 // ---- scalar builtins --------------------------------------------------------------------------
-SBX_FN float sin(float a) { return sbx_sinf(a); }
-SBX_FN float cos(float a) { return sbx_cosf(a); }
-SBX_FN float tan(float a) { return sbx_tanf(a); }
-SBX_FN float exp(float a) { return sbx_expf(a); }
-SBX_FN float pow(float a, float b) { return sbx_powf(a, b); }
-SBX_FN float acos(float a) { return sbx_acosf(a); }
-SBX_FN float atan(float a) { return sbx_atanf(a); }
-SBX_FN float atan(float y, float x) { return sbx_atan2f(y, x); }
+// -DSBX_MATH_OUTLINE: one out-of-line copy of each transcendental per kernel instead of one per call site.  For
+// apps whose scene function is inlined many times (APP_VINYL: 13 688 SASS instructions, 219 KB, instruction-cache
+// bound) the call costs less than the misses; apps with a transcendental in their hot loop keep them inline.
+#ifdef SBX_MATH_OUTLINE
+#define SBX_TRANSCENDENTAL static __device__ __noinline__
+#else
+#define SBX_TRANSCENDENTAL SBX_FN
+#endif
+SBX_TRANSCENDENTAL float sin(float a) { return sbx_sinf(a); }
+SBX_TRANSCENDENTAL float cos(float a) { return sbx_cosf(a); }
+SBX_TRANSCENDENTAL float tan(float a) { return sbx_tanf(a); }
+SBX_TRANSCENDENTAL float exp(float a) { return sbx_expf(a); }
+SBX_TRANSCENDENTAL float pow(float a, float b) { return sbx_powf(a, b); }
+SBX_TRANSCENDENTAL float acos(float a) { return sbx_acosf(a); }
+SBX_TRANSCENDENTAL float atan(float a) { return sbx_atanf(a); }
+SBX_TRANSCENDENTAL float atan(float y, float x) { return sbx_atan2f(y, x); }
 SBX_FN float sqrt(float a) { return __fsqrt_rn(a); }
 SBX_FN float abs(float a) { return fabsf(a); }
 SBX_FN float floor(float a) { return floorf(a); }

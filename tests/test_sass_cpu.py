@@ -50,7 +50,7 @@ def test_native_raytracer_has_no_local_memory():
     o = ops(sass("APP_RAYTRACER.native.cubin"))
     assert not any(x in ("STL", "LDL") for x in o)
     plugin = ops(sass("APP_RAYTRACER.plugin.cubin"))
-    assert plugin.count("STL") > 50                                      # the unchanged header keeps its scene tables in local memory
+    assert plugin.count("STL") > 20                                      # the unchanged header keeps its scene tables in local memory
 
 
 def test_native_planet_fits_the_instruction_cache():
