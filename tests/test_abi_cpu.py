@@ -86,6 +86,40 @@ def test_invalid_arguments_are_rejected_without_a_context():
     assert lib.sbx_create(0, None) == abi.SBX_ERR_INVALID
 
 
+def test_new_entry_points_reject_bad_arguments_without_a_context():
+    """rgba8 / sequence / shared host frame / volume bake: NULL context or buffers are SBX_ERR_INVALID, never a crash."""
+    lib = sbx.lib()
+    p = abi.default_params(8, 8)
+    buf = np.zeros((8, 8, 4), np.float32)
+    b8 = np.zeros((8, 8, 4), np.uint8)
+    t = np.zeros(3, np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    assert lib.sbx_render_host_rgba8(None, C.byref(p), None, vp(b8)) == abi.SBX_ERR_INVALID
+    assert lib.sbx_render_device_rgba8(None, C.byref(p), None, None, None) == abi.SBX_ERR_INVALID
+    assert lib.sbx_render_sequence_host(None, C.byref(p), None, vp(t), 3, vp(buf)) == abi.SBX_ERR_INVALID
+    assert lib.sbx_render_sequence_device(None, C.byref(p), None, vp(t), 3, None, None) == abi.SBX_ERR_INVALID
+    out = C.c_void_p()
+    assert lib.sbx_host_frame_register(None, vp(buf), buf.nbytes, C.byref(out)) == abi.SBX_ERR_INVALID
+    assert lib.sbx_host_frame_unregister(None, vp(buf)) == abi.SBX_ERR_INVALID
+    assert lib.sbx_bake_noise_volume_host(None, 16, 0, 16, vp(buf)) == abi.SBX_ERR_INVALID
+    assert lib.sbx_bake_noise_volume_device(None, 16, 0, 16, None, None) == abi.SBX_ERR_INVALID
+    assert lib.sbx_set_option(None, b"coop_waves_x100", 1) == abi.SBX_ERR_INVALID
+
+
+def test_compile_defines_reach_the_kernel_image(tmp_path, monkeypatch):
+    """SBX_COMPILE_DEFINES: launch shape and out-of-line transcendentals are per-image build knobs (csrc/Makefile)."""
+    hdr = tmp_path / "app_mini.h"
+    hdr.write_text(MINI_APP)
+    sizes = {}
+    for tag, defs in (("inline", ""), ("outline", "SBX_MATH_OUTLINE=1;SBX_MIN_CTAS_PER_SM=8")):
+        monkeypatch.setenv("SBX_COMPILE_DEFINES", defs)
+        img = tmp_path / ("APP_MINI.%s.cubin" % tag)
+        sbx.compile_app(str(hdr), "APP_MINI", str(img))
+        res = subprocess.run(["cuobjdump", "-res-usage", str(img)], capture_output=True, text=True).stdout
+        sizes[tag] = int(re.search(r"REG:(\d+)", res[res.index("sbx_render"):]).group(1))
+    assert sizes["outline"] <= 64          # __launch_bounds__(128, 8) caps the registers at 65536 / (8 * 128)
+
+
 def test_no_cpu_path_without_a_device():
     """On a machine without a B200 the product must refuse, not fall back."""
     import torch
