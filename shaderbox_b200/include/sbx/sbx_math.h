@@ -232,6 +232,37 @@ SBX_MATH_FN float sbx_cosf(float y) {
     return y - y;
 }
 
+// sin and cos of one argument from ONE argument reduction (what glibc's sincosf does with the same
+// kernels).  Each output is bit-identical to sbx_sinf(y) / sbx_cosf(y): same n, same reduced x, same
+// polynomial branch.  The rotation builders of util.h need both values of every angle.
+SBX_MATH_FN void sbx_sincosf(float y, float* sin_out, float* cos_out) {
+    const sbx_u32 bits = sbx_f2u(y);
+    const sbx_u32 top = (bits >> 20) & 0x7ffu;
+    double x = (double)y;
+    if (top < 0x3f4u) {                              // |y| < pi/4: no reduction
+        if (top < 0x398u) { *sin_out = y; *cos_out = 1.0f; return; }
+        const double x2 = x * x;
+        *sin_out = sbx_sincos_poly(x, x2, 0, 0);
+        *cos_out = sbx_sincos_poly(x, x2, 1, 0);
+        return;
+    }
+    if (top >= 0x7f8u) { *sin_out = *cos_out = y - y; return; }   // inf / nan
+    int n, n_sin;
+    if (top < 0x42fu) {                              // |y| < 120
+        x = sbx_reduce_fast(x, &n);
+        n_sin = n;
+    } else {                                         // the sine folds the argument's sign into the quadrant
+        x = sbx_reduce_large(bits, &n);
+        n_sin = n + (int)(bits >> 31);
+    }
+    const double x2 = x * x;
+    const int qs = n_sin & 3, qc = n & 3;
+    const double xs = x * ((qs == 1 || qs == 2) ? -1.0 : 1.0);
+    const double xc = x * ((qc == 1 || qc == 2) ? -1.0 : 1.0);
+    *sin_out = sbx_sincos_poly(xs, x2, n, n_sin & 2);
+    *cos_out = sbx_sincos_poly(xc, x2, n ^ 1, n & 2);
+}
+
 // ---------------------------------------------------------------------------------------------
 // expf   (e_expf.c, N = 32, degree-3 polynomial)
 // ---------------------------------------------------------------------------------------------

@@ -188,6 +188,9 @@ SBX_FN float2 pk_mix(float2 x, float2 y, float2 one_minus_a, float2 a) { return 
 #endif
 SBX_TRANSCENDENTAL float sin(float a) { return sbx_sinf(a); }
 SBX_TRANSCENDENTAL float cos(float a) { return sbx_cosf(a); }
+// both at once from one argument reduction; each equals sin(a) / cos(a) bit for bit (sbx_math.h, sbx_sincosf)
+struct sbx_sincos_t { float s, c; };
+SBX_TRANSCENDENTAL sbx_sincos_t sbx_sincos(float a) { sbx_sincos_t r; sbx_sincosf(a, &r.s, &r.c); return r; }
 SBX_TRANSCENDENTAL float tan(float a) { return sbx_tanf(a); }
 SBX_TRANSCENDENTAL float exp(float a) { return sbx_expf(a); }
 SBX_TRANSCENDENTAL float pow(float a, float b) { return sbx_powf(a, b); }

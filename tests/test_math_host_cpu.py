@@ -19,7 +19,7 @@ def exe(tmp_path_factory):
 
 
 @pytest.mark.parametrize("fn,stride", [("sinf", 257), ("cosf", 257), ("expf", 257), ("powf", 257), ("tanf", 257),
-                                       ("acosf", 257), ("atanf", 257), ("atan2f", 257)])
+                                       ("acosf", 257), ("atanf", 257), ("atan2f", 257), ("sincosf", 257)])
 def test_bit_identical_to_libm(exe, fn, stride):
     r = subprocess.run([exe, fn, str(stride), "8"], capture_output=True, text=True)
     rep = json.loads(r.stdout)
