@@ -76,7 +76,7 @@ __device__ __forceinline__ void sbx_stage_lut(const void* lut_global) {
 
 namespace sbx_glsl {
 
-// uniform loaders used by uniform_buffer.h's _uniform()
+// uniform loaders used by uniform_buffer.h's SBX_UNIFORM()
 SBX_FN float sbx_uniform(const float& v) { return v; }
 SBX_FN int sbx_uniform(const int& v) { return v; }
 SBX_FN vec3 sbx_uniform(const float (&v)[3]) { return vec3(v[0], v[1], v[2]); }
