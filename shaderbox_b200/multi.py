@@ -8,6 +8,8 @@ Rank 0 then scatters every part to its frame rows (sbx_unshard_device on the GPU
 
 This module is plumbing: it never computes a pixel.
 """
+import time
+
 import torch
 import torch.distributed as dist
 
@@ -188,6 +190,7 @@ class SharedHostFrame:
         self.array = np.frombuffer(self._map, dtype=np.float32, count=self.width * self.height * 4).reshape(self.height, self.width, 4)
         self._slots = np.frombuffer(self._map, dtype=np.int64, count=self.world, offset=frame_bytes)
         self._epoch = 0
+        self.timeout_s = 120.0                                  # a rank that died must not leave the others spinning forever
         self.host_ptr = self.array.ctypes.data
         self.alias = renderer.host_frame_register(self.host_ptr, frame_bytes)
         if self.world > 1:
@@ -198,18 +201,25 @@ class SharedHostFrame:
     def render(self, params, stripe_rows=DEFAULT_STRIPE_ROWS):
         """One frame, synchronous: on return (every rank) the frame is complete in host memory (self.array)."""
         assert params.width == self.width and params.height == self.height
-        dev = torch.device("cuda", self.renderer.device)
-        stream = torch.cuda.current_stream(dev)
-        self.renderer.render_frame(params, self.alias, shard=shard_of(self.rank, self.world, stripe_rows), stream=stream.cuda_stream)
-        stream.synchronize()                                    # this rank's stripes are in host memory
+        stream = torch.cuda.current_stream(torch.device("cuda", self.renderer.device)) if torch.cuda.is_available() else None
+        self.renderer.render_frame(params, self.alias, shard=shard_of(self.rank, self.world, stripe_rows),
+                                   stream=stream.cuda_stream if stream is not None else 0)
+        if stream is not None:
+            stream.synchronize()                                # this rank's stripes are in host memory
+        t_wait = time.monotonic()
         self._epoch += 1
         self._slots[self.rank] = self._epoch
         slots, epoch = self._slots, self._epoch
+        spins = 0
         while int(slots.min()) < epoch:                         # host barrier on the control page
-            pass
+            spins += 1
+            if (spins & 0xfffff) == 0 and time.monotonic() - t_wait > self.timeout_s:
+                raise RuntimeError("SharedHostFrame: rank(s) %s did not finish frame %d within %.0f s"
+                                   % ([r for r in range(self.world) if int(slots[r]) < epoch], epoch, self.timeout_s))
 
     def close(self):
-        torch.cuda.synchronize()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier(self.group)
         self.renderer.host_frame_unregister(self.host_ptr)

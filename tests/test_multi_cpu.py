@@ -61,3 +61,61 @@ def test_single_rank_is_identity():
     assert multi.part_rows(H, multi.shard_of(0, 1)) == H
     out = multi.assemble_rows([full], W, H, 4)
     assert bits_equal(out.numpy(), full.numpy())
+
+
+class _OracleHostRenderer:
+    """Stands in for shaderbox_b200.Renderer in the shared-host-frame protocol test: "registering" the frame returns its
+    own address and render_frame writes this rank's rows (from the CPU oracle) at their frame positions -- what the
+    render kernel's zero-copy stores do on a GPU box."""
+
+    device = 0
+
+    def __init__(self, app):
+        self.app = app
+
+    def host_frame_register(self, host_ptr, nbytes):
+        self.ptr = host_ptr
+        return host_ptr
+
+    def host_frame_unregister(self, host_ptr):
+        assert host_ptr == self.ptr
+
+    def render_frame(self, params, alias, shard, stream=0):
+        import ctypes
+
+        from shaderbox_b200.abi import shard_rows
+
+        rows = shard_rows(shard[0], shard[1], shard[2], params.height)
+        part = loader.oracle_render(self.app, params, shard=Shard(*shard), nthreads=1)
+        frame = np.ctypeslib.as_array(ctypes.cast(alias, ctypes.POINTER(ctypes.c_float)), shape=(params.height, params.width, 4))
+        if rows:
+            frame[rows] = part
+
+
+def _host_frame_worker(rank, world, port, stripe, result_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shost = multi.SharedHostFrame(_OracleHostRenderer(APP), W, H)
+        for frame_no, t in enumerate((T, T + 1.0)):             # two frames: the barrier epoch advances
+            if rank == 0:
+                shost.array[:] = np.nan
+            dist.barrier()
+            shost.render(default_params(W, H, t), stripe)
+            if rank == 0:
+                np.save(result_path % frame_no, np.array(shost.array))
+            dist.barrier()
+        shost.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,stripe", [(2, 4), (3, 1)])
+def test_shared_host_frame_protocol(tmp_path, world, stripe):
+    """One POSIX-shm frame mapped by every rank, each rank writing its own stripes, completion by the host barrier on
+    the control page: on return from render() rank 0 reads the whole frame."""
+    result = str(tmp_path / "host%d.npy")
+    mp.spawn(_host_frame_worker, args=(world, _free_port(), stripe, result), nprocs=world, join=True)
+    for frame_no, t in enumerate((T, T + 1.0)):
+        assert bits_equal(np.load(result % frame_no), loader.oracle_render(APP, default_params(W, H, t)))
