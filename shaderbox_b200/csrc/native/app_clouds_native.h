@@ -130,20 +130,20 @@ SBX_FN float density_view(float2 pos_xy, float pos_z) {
     return sbx_density_of(t);
 }
 
+// exp(-density * sigma * dt) of :110 and :135 (Beer-Lambert)
+SBX_FN float sbx_beer_lambert(float density, float dt) { return exp(-density * sigma_scattering * dt); }
+
 // illuminate_volume (:91-123).  `origin` is the view sample just evaluated by density_view, so
-// the memo holds its slices.  Per light sample: the z chain of the four octaves, their lattice
-// cells, and -- if x and y still equal the memo's -- only the octaves that left their cell are
-// re-sliced.  Then every octave is one weight and one mix of its two slices, two octaves per
-// instruction.
+// the memo holds its slices.  Per light sample: the z chain of the four octaves, their position in the
+// memoised lattice cells, and -- if x and y still equal the memo's -- only the octaves that left their
+// cell are re-sliced.  Then every octave is one weight (two octaves per FFMA2) and one mix of its two slices.
 SBX_FN float illuminate_volume(float2 origin_xy, float origin_z, _in(vec3) L) {
     const float dt = cld_thick / float(cld_march_steps);
     const vec3 step = L * dt;
     float2 pos_xy = pk_add(origin_xy, pk(step.x, step.y));     // don't sample just where the main raymarcher is
     float pos_z = origin_z + step.z;
     float transmittance = 1.0f;
-    // slices transposed to octave pairs: (y0 of octave 0, y0 of octave 1), ...
-    float2 a01 = pk(sbx_ys0.x, sbx_ys1.x), b01 = pk(sbx_ys0.y, sbx_ys1.y);
-    float2 a23 = pk(sbx_ys2.x, sbx_ys3.x), b23 = pk(sbx_ys2.y, sbx_ys3.y);
+    float2 ys0 = sbx_ys0, ys1 = sbx_ys1, ys2 = sbx_ys2, ys3 = sbx_ys3;
     float2 m01 = pk(sbx_mz0, sbx_mz1), m23 = pk(sbx_mz2, sbx_mz3);
     for (int i = 0; i < illum_march_steps; i++) {
         const float z0 = pos_z * cld_noise_factor * 2.03f;     // the z chain of p = pos*.001*2.03, p *= 2.64
@@ -163,39 +163,40 @@ SBX_FN float illuminate_volume(float2 origin_xy, float origin_z, _in(vec3) L) {
             float2 cxy;
             if (!(same_xy && c01.x == m01.x)) {
                 cxy = pk(floor(pxy.x), floor(pxy.y));
-                const float2 ys = sbx_slices(cxy, c01.x, sbx_noise_weight(pk_sub(pxy, cxy)));
-                a01.x = ys.x; b01.x = ys.y; m01.x = c01.x;
+                ys0 = sbx_slices(cxy, c01.x, sbx_noise_weight(pk_sub(pxy, cxy)));
+                m01.x = c01.x;
             }
             pxy = pk_mul(pxy, 2.64f);
             if (!(same_xy && c01.y == m01.y)) {
                 cxy = pk(floor(pxy.x), floor(pxy.y));
-                const float2 ys = sbx_slices(cxy, c01.y, sbx_noise_weight(pk_sub(pxy, cxy)));
-                a01.y = ys.x; b01.y = ys.y; m01.y = c01.y;
+                ys1 = sbx_slices(cxy, c01.y, sbx_noise_weight(pk_sub(pxy, cxy)));
+                m01.y = c01.y;
             }
             pxy = pk_mul(pxy, 2.64f);
             if (!(same_xy && c23.x == m23.x)) {
                 cxy = pk(floor(pxy.x), floor(pxy.y));
-                const float2 ys = sbx_slices(cxy, c23.x, sbx_noise_weight(pk_sub(pxy, cxy)));
-                a23.x = ys.x; b23.x = ys.y; m23.x = c23.x;
+                ys2 = sbx_slices(cxy, c23.x, sbx_noise_weight(pk_sub(pxy, cxy)));
+                m23.x = c23.x;
             }
             pxy = pk_mul(pxy, 2.64f);
             if (!(same_xy && c23.y == m23.y)) {
                 cxy = pk(floor(pxy.x), floor(pxy.y));
-                const float2 ys = sbx_slices(cxy, c23.y, sbx_noise_weight(pk_sub(pxy, cxy)));
-                a23.y = ys.x; b23.y = ys.y; m23.y = c23.y;
+                ys3 = sbx_slices(cxy, c23.y, sbx_noise_weight(pk_sub(pxy, cxy)));
+                m23.y = c23.y;
             }
             sbx_mx = pos_xy.x; sbx_my = pos_xy.y;
             f01 = pk_sub(z01, m01); f23 = pk_sub(z23, m23);
         }
         const float2 w01 = sbx_noise_weight(f01), w23 = sbx_noise_weight(f23);
-        const float2 n01 = pk_mix(a01, b01, pk_one_minus(w01), w01);          // noise_iq of octaves 0, 1
-        const float2 n23 = pk_mix(a23, b23, pk_one_minus(w23), w23);          // octaves 2, 3
-        const float2 s01 = pk_mul(n01, pk(.5f, .25f)), s23 = pk_mul(n23, pk(.125f, .0625f));
-        const float density = sbx_density_of(((s01.x + s01.y) + s23.x) + s23.y);
+        const float2 a01 = pk_one_minus(w01), a23 = pk_one_minus(w23);
+        // noise_iq of each octave = mix(y0, y1, w) on its two memoised slices, then the fbm sum (src/fbm.h:6)
+        const float n0 = ys0.x * a01.x + ys0.y * w01.x, n1 = ys1.x * a01.y + ys1.y * w01.y;
+        const float n2 = ys2.x * a23.x + ys2.y * w23.x, n3 = ys3.x * a23.y + ys3.y * w23.y;
+        const float density = sbx_density_of(((n0 * .5f + n1 * .25f) + n2 * .125f) + n3 * .0625f);
 #ifdef SBX_X_NOEXP
         if (density != 0.0f) transmittance *= (1.0f - density * sigma_scattering * dt);
 #else
-        transmittance *= exp(-density * sigma_scattering * dt);   // branch-free: an empty sample multiplies by exp(-0) == 1
+        transmittance *= sbx_beer_lambert(density, dt);   // branch-free: an empty sample multiplies by exp(-0) == 1
 #endif
         pos_xy = pk_add(pos_xy, pk(step.x, step.y));
         pos_z += step.z;
@@ -224,7 +225,7 @@ SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-202
         t += dt;
         const float density = density_view(pos_xy, pos_z);
         if (!(density < .005f)) {                                          // integrate_volume, :125-148
-            const float T_i = exp(-density * sigma_scattering * dt);       // Beer-Lambert
+            const float T_i = sbx_beer_lambert(density, dt);               // Beer-Lambert
             transmittance *= T_i;
 #ifdef SBX_X_NOLIGHT
             radiance += (density * sigma_scattering) * (sbx_ys0.x + sbx_ys1.y + sbx_ys2.x + sbx_ys3.y + sbx_mz0 + sbx_mz1 + sbx_mz2 + sbx_mz3) * transmittance * dt;
@@ -279,7 +280,7 @@ SBX_FN vec4 render_clouds_coop(_in(ray_t) eye, bool active) {
             const float pos_z = origin.z + t * projection.z;
             const float density = density_view(pos_xy, pos_z);
             if (!(density < .005f)) {
-                T_i = exp(-density * sigma_scattering * dt);
+                T_i = sbx_beer_lambert(density, dt);
                 A = (density * sigma_scattering) * illuminate_volume(pos_xy, pos_z, sun_dir);
             }
         }

@@ -266,19 +266,13 @@ SBX_MATH_FN void sbx_sincosf(float y, float* sin_out, float* cos_out) {
 // ---------------------------------------------------------------------------------------------
 // expf   (e_expf.c, N = 32, degree-3 polynomial)
 // ---------------------------------------------------------------------------------------------
-SBX_MATH_FN float sbx_expf(float x) {
+// the main path of expf: valid for |x| < 88 (biased exponent field <= 0x42a), where none of the special cases
+// below can apply.  Callers that can bound their argument (a march loop whose optical depth per step is bounded by
+// its uniforms) call this directly and save the range test per call.
+SBX_MATH_FN float sbx_expf_core(float x) {
     const double InvLn2N = 0x1.71547652b82fep+5, Shift = 0x1.8p52;
     const double C0 = 0x1.c6af84b912394p-20, C1 = 0x1.ebfce50fac4f3p-13, C2 = 0x1.62e42ff0c52d6p-6;
     const double xd = (double)x;
-    const sbx_u32 top = (sbx_f2u(x) >> 20) & 0x7ffu;
-    if (top > 0x42au) {                                      // |x| >= 88 or nan
-        if (sbx_f2u(x) == 0xff800000u) return 0.0f;           // exp(-inf)
-        if (top > 0x7f7u) return x + x;                       // +inf, nan
-        if (x > 0x1.62e42ep6f) return sbx_u2f(0x7f800000u);   // overflow
-        if (x < -0x1.9fe368p6f) return 0.0f;                  // underflow to zero
-        if (x < -0x1.9d1d9ep6f) return 0x1p-149f;             // __math_may_uflowf: 0x1.4p-75f squared
-        // -0x1.9d1d9ep6 <= x <= -88 falls through: subnormal result, rounded once from double
-    }
     double kd = sbx_fma(InvLn2N, xd, Shift);
     const sbx_u64 ki = sbx_d2u(kd);
     kd -= Shift;
@@ -292,6 +286,19 @@ SBX_MATH_FN float sbx_expf(float x) {
     yv = sbx_fma(z, r2, yv);
     yv = yv * s;
     return sbx_d2f(yv);
+}
+
+SBX_MATH_FN float sbx_expf(float x) {
+    const sbx_u32 top = (sbx_f2u(x) >> 20) & 0x7ffu;
+    if (top > 0x42au) {                                      // |x| >= 88 or nan
+        if (sbx_f2u(x) == 0xff800000u) return 0.0f;           // exp(-inf)
+        if (top > 0x7f7u) return x + x;                       // +inf, nan
+        if (x > 0x1.62e42ep6f) return sbx_u2f(0x7f800000u);   // overflow
+        if (x < -0x1.9fe368p6f) return 0.0f;                  // underflow to zero
+        if (x < -0x1.9d1d9ep6f) return 0x1p-149f;             // __math_may_uflowf: 0x1.4p-75f squared
+        // -0x1.9d1d9ep6 <= x <= -88 falls through: subnormal result, rounded once from double
+    }
+    return sbx_expf_core(x);
 }
 
 // ---------------------------------------------------------------------------------------------
