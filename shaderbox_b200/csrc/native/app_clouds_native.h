@@ -130,14 +130,19 @@ SBX_FN float density_view(float2 pos_xy, float pos_z) {
     return sbx_density_of(t);
 }
 
-// exp(-density * sigma * dt) of :110 and :135 (Beer-Lambert)
-SBX_FN float sbx_beer_lambert(float density, float dt) { return exp(-density * sigma_scattering * dt); }
+// exp(-density * sigma * dt) of :110 and :135 (Beer-Lambert).  density lies in [0, 1) (noise values times gains
+// that add up to .9375), so |argument| <= |sigma * dt|: when that is below 80 -- decided once per ray, render()
+// picks the BOUNDED instantiation of the march -- expf's range test cannot fire and its main path is called directly.
+template <bool BOUNDED> SBX_FN float sbx_beer_lambert(float density, float dt) {
+    const float x = -density * sigma_scattering * dt;
+    return BOUNDED ? sbx_expf_core(x) : exp(x);
+}
 
 // illuminate_volume (:91-123).  `origin` is the view sample just evaluated by density_view, so
 // the memo holds its slices.  Per light sample: the z chain of the four octaves, their position in the
 // memoised lattice cells, and -- if x and y still equal the memo's -- only the octaves that left their
 // cell are re-sliced.  Then every octave is one weight (two octaves per FFMA2) and one mix of its two slices.
-SBX_FN float illuminate_volume(float2 origin_xy, float origin_z, _in(vec3) L) {
+template <bool BOUNDED> SBX_FN float illuminate_volume(float2 origin_xy, float origin_z, _in(vec3) L) {
     const float dt = cld_thick / float(cld_march_steps);
     const vec3 step = L * dt;
     float2 pos_xy = pk_add(origin_xy, pk(step.x, step.y));     // don't sample just where the main raymarcher is
@@ -196,7 +201,7 @@ SBX_FN float illuminate_volume(float2 origin_xy, float origin_z, _in(vec3) L) {
 #ifdef SBX_X_NOEXP
         if (density != 0.0f) transmittance *= (1.0f - density * sigma_scattering * dt);
 #else
-        transmittance *= sbx_beer_lambert(density, dt);   // branch-free: an empty sample multiplies by exp(-0) == 1
+        transmittance *= sbx_beer_lambert<BOUNDED>(density, dt);   // branch-free: an empty sample multiplies by exp(-0) == 1
 #endif
         pos_xy = pk_add(pos_xy, pk(step.x, step.y));
         pos_z += step.z;
@@ -204,7 +209,7 @@ SBX_FN float illuminate_volume(float2 origin_xy, float origin_z, _in(vec3) L) {
     return transmittance * sun_power * sbx_phase;
 }
 
-SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-202
+template <bool BOUNDED> SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-202
     const vec3 projection = eye.direction / eye.direction.y;
     vec3 origin = eye.origin + projection * 150.0f;
     origin += wind_dir * u_time * (1.0f / cld_noise_factor);
@@ -225,12 +230,12 @@ SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-202
         t += dt;
         const float density = density_view(pos_xy, pos_z);
         if (!(density < .005f)) {                                          // integrate_volume, :125-148
-            const float T_i = sbx_beer_lambert(density, dt);               // Beer-Lambert
+            const float T_i = sbx_beer_lambert<BOUNDED>(density, dt);      // Beer-Lambert
             transmittance *= T_i;
 #ifdef SBX_X_NOLIGHT
             radiance += (density * sigma_scattering) * (sbx_ys0.x + sbx_ys1.y + sbx_ys2.x + sbx_ys3.y + sbx_mz0 + sbx_mz1 + sbx_mz2 + sbx_mz3) * transmittance * dt;
 #else
-            radiance += (density * sigma_scattering) * illuminate_volume(pos_xy, pos_z, sun_dir) * transmittance * dt;
+            radiance += (density * sigma_scattering) * illuminate_volume<BOUNDED>(pos_xy, pos_z, sun_dir) * transmittance * dt;
 #endif
             alpha += (1.0f - T_i) * (1.0f - alpha);
         }
@@ -251,7 +256,7 @@ SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-202
 // P times shorter: frames that are small for the machine (one GPU's share of a 1080p frame at 8
 // GPUs is ~2 waves of warps) no longer end in a long single-warp tail, and the lanes of a warp
 // sit on neighbouring steps of the same rays, which keeps their branches and table lines together.
-SBX_FN vec4 render_clouds_coop(_in(ray_t) eye, bool active) {
+template <bool BOUNDED> SBX_FN vec4 render_clouds_coop(_in(ray_t) eye, bool active) {
     const int P = SBX_LANES_PER_PIXEL;
     const int lane = threadIdx.x & 31, phase = lane % P, base = lane - phase;
     const vec3 projection = eye.direction / eye.direction.y;
@@ -280,8 +285,8 @@ SBX_FN vec4 render_clouds_coop(_in(ray_t) eye, bool active) {
             const float pos_z = origin.z + t * projection.z;
             const float density = density_view(pos_xy, pos_z);
             if (!(density < .005f)) {
-                T_i = sbx_beer_lambert(density, dt);
-                A = (density * sigma_scattering) * illuminate_volume(pos_xy, pos_z, sun_dir);
+                T_i = sbx_beer_lambert<BOUNDED>(density, dt);
+                A = (density * sigma_scattering) * illuminate_volume<BOUNDED>(pos_xy, pos_z, sun_dir);
             }
         }
 #pragma unroll
@@ -360,13 +365,15 @@ static __device__ __noinline__ float4 sbx_generic_pixel(const sbx_launch* L, flo
 SBX_FN vec3 render(_in(ray_t) eye_ray, _in(vec3) point_cam) {   // :204-218
     const vec3 sky = render_sky_color(eye_ray.direction);
     sbx_kmax = 0u;
+    const bool bounded = abs(sigma_scattering * (cld_thick / float(cld_march_steps))) < 80.0f;   // see sbx_beer_lambert
 #if SBX_LANES_PER_PIXEL > 1
     const bool below = dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f;
-    vec4 cld = render_clouds_coop(eye_ray, !below);                     // every lane of the warp takes part in the shuffles
+    // (the uniforms, hence `bounded`, are the same in every lane: the whole warp takes one instantiation)
+    vec4 cld = bounded ? render_clouds_coop<true>(eye_ray, !below) : render_clouds_coop<false>(eye_ray, !below);
     if (below) return sky;
 #else
     if (dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f) return sky;
-    vec4 cld = render_clouds(eye_ray);
+    vec4 cld = bounded ? render_clouds<true>(eye_ray) : render_clouds<false>(eye_ray);
 #endif
     if (sbx_kmax >= (unsigned)sbx_L->hash_span) {                       // table miss: redo the pixel
         const float4 g = sbx_generic_pixel(sbx_L, eye_ray.origin.x, eye_ray.origin.y, eye_ray.origin.z,

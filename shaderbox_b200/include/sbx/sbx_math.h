@@ -269,9 +269,25 @@ SBX_MATH_FN void sbx_sincosf(float y, float* sin_out, float* cos_out) {
 // the main path of expf: valid for |x| < 88 (biased exponent field <= 0x42a), where none of the special cases
 // below can apply.  Callers that can bound their argument (a march loop whose optical depth per step is bounded by
 // its uniforms) call this directly and save the range test per call.
+#if defined(SBX_DEVICE_CODE) && defined(SBX_EXPF_CONSTANT_BANK)
+// -DSBX_EXPF_CONSTANT_BANK (kernels with expf in their hot loop: native APP_CLOUDS): the four double constants live
+// in constant memory and are fetched with one LDC.64 each, whereas a 64-bit immediate with a non-zero low word
+// costs two moves per use (8 of the ~40 instructions of an inlined expf, seven times per in-cloud march step).
+// It costs registers, so kernels that call expf once per pixel keep the immediates (PLANET, RAYTRACER: -3 %).
+__constant__ double sbx_expf_k[4] = {0x1.71547652b82fep+5, 0x1.c6af84b912394p-20, 0x1.ebfce50fac4f3p-13, 0x1.62e42ff0c52d6p-6};
+#define SBX_EXPF_INVLN2N sbx_expf_k[0]
+#define SBX_EXPF_C0 sbx_expf_k[1]
+#define SBX_EXPF_C1 sbx_expf_k[2]
+#define SBX_EXPF_C2 sbx_expf_k[3]
+#else
+#define SBX_EXPF_INVLN2N 0x1.71547652b82fep+5
+#define SBX_EXPF_C0 0x1.c6af84b912394p-20
+#define SBX_EXPF_C1 0x1.ebfce50fac4f3p-13
+#define SBX_EXPF_C2 0x1.62e42ff0c52d6p-6
+#endif
 SBX_MATH_FN float sbx_expf_core(float x) {
-    const double InvLn2N = 0x1.71547652b82fep+5, Shift = 0x1.8p52;
-    const double C0 = 0x1.c6af84b912394p-20, C1 = 0x1.ebfce50fac4f3p-13, C2 = 0x1.62e42ff0c52d6p-6;
+    const double InvLn2N = SBX_EXPF_INVLN2N, Shift = 0x1.8p52;
+    const double C0 = SBX_EXPF_C0, C1 = SBX_EXPF_C1, C2 = SBX_EXPF_C2;
     const double xd = (double)x;
     double kd = sbx_fma(InvLn2N, xd, Shift);
     const sbx_u64 ki = sbx_d2u(kd);
