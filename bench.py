@@ -423,7 +423,7 @@ def fp32_issue(workload, kernel_ms, sm_max_mhz, clocks):
     from shaderbox_b200.abi import Shard, default_params
 
     app, w, h, t, ov = WORKLOADS[workload]
-    if not (loader.have_oracle() and app not in ("APP_SDF_AO", "APP_VINYL")):
+    if not loader.have_oracle():
         return None
     parts = max(1, h // 16)
     rows = len(range(parts // 2, h, parts))

@@ -4,7 +4,7 @@
  * this file.  It is never linked into, called from or shipped with the product (libsbx.so).
  *
  * What it restates: per-pixel mainImage (src/main.h:6-53) of APP_EGG, APP_CLOUDS,
- * APP_ATMOSPHERE, APP_PLANET and APP_RAYTRACER together with the operator headers they use
+ * APP_ATMOSPHERE, APP_PLANET, APP_RAYTRACER, APP_SDF_AO and APP_VINYL together with the operator headers they use
  * (util.h, intersect.h, sdf.h, IK.h, noise_iq.h, fbm.h, volumetric.h, material.h, light.h,
  * util_optics.h, cornell_box.h).  Every function cites the reference lines it follows.
  *
@@ -811,6 +811,375 @@ static void egg_pixel(const uniforms_t* u, float fx, float fy, float out[4]) {  
     main_image(u, egg_render, V3(.0f, .25f, 5.25f), V3(.0f, .25f, .0f), 1.0f, fx, fy, out);
 }
 
+/* ================================== APP_SDF_AO (src/app_sdf_ao.h) ============================= */
+static inline float sd_box(v3 p, v3 b) {                                          /* src/sdf.h:67-73 */
+    return g_max(fabsf(p.x) - b.x, g_max(fabsf(p.y) - b.y, fabsf(p.z) - b.z));
+}
+static inline float sd_y_cylinder(v3 p, float r, float h) {                       /* src/sdf.h:85-93 */
+    return g_max(len2(V2(p.x, p.z)) - r, fabsf(p.y) - h / 2.0f);
+}
+static inline float op_sub1(float d1, float d2) { return g_max(d1, -d2); }        /* src/sdf.h:20-28 */
+static inline float g_mod(float a, float b) { return a - b * floorf(a / b); }     /* GLSL mod */
+static float checkboard_pattern(v2 pos, float scale) {                            /* src/util.h:95-101 */
+    v2 pattern = V2(floorf(pos.x * scale), floorf(pos.y * scale));
+    return g_mod(pattern.x + pattern.y, 2.0f);
+}
+enum { AO_MAT_DEBUG = 0, AO_MAT_GROUND, AO_MAT_PIPE, AO_MAT_BOTTOM, AO_MAT_DECK, AO_MAT_COPING };   /* :14-19 */
+static const v3 ao_size = {1.3f, 1.0f, 1.25f};                                    /* :53 */
+
+static v2 ao_sdf_pipe(v3 pos) {                                                   /* :55-116 */
+    const v3 size = ao_size;
+    /* ramp: box minus a lying cylinder */
+    v3 p = sub3(pos, V3(0, size.y, 0));
+    float b = sd_box(p, size);
+    p = sub3(p, V3(.7f, .5f, 0));
+    p = vec_mat(p, rotate_around_x(-90.0f));
+    float c = sd_y_cylinder(p, size.y + .55f, 2.0f * size.z + .1f);
+    v2 pipe = V2(op_sub1(b, c), (float)AO_MAT_PIPE);
+    /* coping bar */
+    p = sub3(pos, V3(0, size.y, 0));
+    p = sub3(p, V3(-size.x + .525f, size.y, 0));
+    p = vec_mat(p, rotate_around_x(-90.0f));
+    v2 coping = V2(sd_y_cylinder(p, .025f, 2.0f * size.z), (float)AO_MAT_COPING);
+    /* deck railing */
+    p = sub3(pos, V3(0, size.y * 2.0f, 0));
+    float rail = sd_box(add3(p, V3(size.x, -.25f, 0)), V3(.025f, .05f, size.z));
+    const v3 B = {.025f, .125f, .025f};
+    const float H = -.125f;
+    float bar_1 = sd_box(add3(p, V3(size.x, H, 0)), B);
+    float bar_2 = sd_box(add3(p, V3(size.x, H, size.z / 2.0f)), B);
+    float bar_3 = sd_box(add3(p, V3(size.x, H, size.z)), B);
+    float bar_4 = sd_box(add3(p, V3(size.x, H, -size.z / 2.0f)), B);
+    float bar_5 = sd_box(add3(p, V3(size.x, H, -size.z)), B);
+    float b_a = g_min(bar_1, bar_2);
+    float b_b = g_min(b_a, bar_3);
+    float b_c = g_min(bar_4, bar_5);
+    float bars = g_min(b_b, b_c);
+    v2 railing = V2(g_min(rail, bars), (float)AO_MAT_DECK);
+    v2 deck = op_add2(railing, coping);
+    return op_add2(pipe, deck);
+}
+static v2 ao_sdf(v3 pos) {                                                        /* :118-157 */
+    const v3 size = ao_size;
+    const float B = .15f;
+    v3 p = sub3(pos, V3(0, B, 0));
+    v2 bottom = V2(sd_box(p, V3(2.25f * size.x, B, size.z)), (float)AO_MAT_BOTTOM);
+    v2 pipe1 = ao_sdf_pipe(add3(p, V3(1.25f * size.x, 0, 0)));
+    p = sub3(p, V3(1.25f * size.x, 0, 0));
+    p = vec_mat(p, rotate_around_y(180.0f));
+    v2 pipe2 = ao_sdf_pipe(p);
+    v2 pipe = op_add2(pipe1, pipe2);
+    v2 ref = V2(sd_box(pos, V3(.025f, 15.0f, .025f)), (float)AO_MAT_DEBUG);
+    v2 ground = V2(sd_plane(pos, V3(0, 1, 0), 0.0f), (float)AO_MAT_GROUND);
+    v2 g = op_add2(ground, ref);
+    v2 b = op_add2(pipe, bottom);
+    return op_add2(b, g);
+}
+static v3 ao_sdf_normal(v3 p) {                                                   /* :159-170 */
+    const float dt = 0.001f;
+    v3 x = V3(dt, 0, 0), y = V3(0, dt, 0), z = V3(0, 0, dt);
+    return norm3(V3(ao_sdf(add3(p, x)).x - ao_sdf(sub3(p, x)).x,
+                    ao_sdf(add3(p, y)).x - ao_sdf(sub3(p, y)).x,
+                    ao_sdf(add3(p, z)).x - ao_sdf(sub3(p, z)).x));
+}
+static float ao_occlusion(const hit_t* hit) {                                     /* sdf_ao, :172-188 (.x of its grey) */
+    const float dt = .5f;
+    const int steps = 5;
+    float occlusion = 0.0f;
+    for (float i = 1.0f; i <= (float)steps; i += 1.0f) {
+        v3 p = add3(hit->origin, rscale3(dt * i, hit->normal));
+        float d = ao_sdf(p).x;
+        occlusion += 1.0f / m_pow(2.0f, i) * (dt * i - d);
+    }
+    return 1.0f - g_clamp(occlusion, 0.0f, 1.0f);
+}
+static v3 ao_illuminate(v3 eye, const hit_t* hit, float ao, float sh) {           /* :216-250 */
+    const v3 sun_dir = norm3(V3(1, 2, 1));                                        /* :214 */
+    v3 accum = V3(0, 0, 0);
+    float sun_ray = g_max(0.0f, dot3(sun_dir, hit->normal));                      /* key light */
+    accum = add3(accum, rscale3(sh * sun_ray, V3(1.2f, 1.3f, 1.0f)));
+    float h = hit->normal.y;                                                      /* fill 1: faked hemisphere */
+    accum = add3(accum, rscale3(ao * h, V3(.15f, .15f, .4f)));
+    float ind = g_max(0.0f, dot3(mul3(sun_dir, V3(-1, 0, -1)), hit->normal));     /* fill 2: indirect */
+    accum = add3(accum, rscale3(ao * ind, V3(.4f, .28f, .2f)));
+    v3 materials[6];                                                              /* setup_scene, :35-43 */
+    materials[AO_MAT_DEBUG] = V3(1, 1, 1);
+    materials[AO_MAT_GROUND] = V3(0, .2f, 0);
+    materials[AO_MAT_PIPE] = V3(.1f, .1f, .1f);
+    materials[AO_MAT_BOTTOM] = materials[AO_MAT_PIPE];
+    materials[AO_MAT_DECK] = materials[AO_MAT_PIPE];
+    materials[AO_MAT_COPING] = V3(.4f, .4f, .4f);
+    v3 mat_c = V3(0, 0, 0);                                                       /* get_material, :22-33: unset outside 0..5 */
+    if (hit->material_id >= 0 && hit->material_id < 6) mat_c = materials[hit->material_id];
+    if (hit->material_id == AO_MAT_GROUND) {
+        float cb = checkboard_pattern(V2(hit->origin.x, hit->origin.z), .5f);
+        mat_c = mix3(sub3(mat_c, rscale3(.15f, mat_c)), add3(mat_c, rscale3(.15f, mat_c)), cb);
+    }
+    (void)eye;                                                                    /* V is computed and unused, :224 */
+    return mul3(accum, mat_c);
+}
+typedef struct { v3 rgb; float w; } v4c;
+static v4c ao_render_impl(ray_t ray) {                                            /* :252-294 */
+    const int steps = 70;
+    const float end = 20.0f;
+    float t = 0.0f;
+    v4c r;
+    for (int i = 0; i < steps; i++) {
+        v3 p = add3(ray.origin, scale3(ray.direction, t));
+        v2 d = ao_sdf(p);
+        if (t > end) break;
+        if (d.x < .005f) {
+            hit_t h;
+            h.t = t;
+            h.material_id = (int)d.y;
+            h.normal = ao_sdf_normal(p);
+            h.origin = p;
+            float ao = ao_occlusion(&h);
+            float sh = 1.0f;
+            r.rgb = ao_illuminate(ray.origin, &h, ao, sh);
+            r.w = t;
+            return r;
+        }
+        t += d.x;
+    }
+    r.rgb = V3(.1f, .1f, .7f);                                                    /* background, :9-12 */
+    r.w = t;
+    return r;
+}
+static v3 ao_render(const uniforms_t* u, ray_t ray, v3 point_cam) {               /* :296-320: exponential height fog */
+    (void)point_cam;
+    v4c orig = ao_render_impl(ray);
+    const float t = orig.w;
+    const v3 fog_color = V3(1, 1, 1);
+    const float density = u->p->fog_density, falloff = u->p->fog_falloff;
+    float fog_factor = density * m_exp(-ray.origin.y * falloff) * (1.0f - m_exp(-t * ray.direction.y * falloff)) /
+                       (ray.direction.y * falloff);
+    return abs3(mix3(orig.rgb, fog_color, fog_factor));
+}
+static void sdf_ao_pixel(const uniforms_t* u, float fx, float fy, float out[4]) {  /* setup_camera :45-50, FOV 1. */
+    m3 rot = rotate_around_y(u->time * 50.0f);
+    v3 eye = mat_vec(rot, V3(0, 3, 5));
+    main_image(u, ao_render, eye, V3(0, 0, 0), 1.0f, fx, fy, out);
+}
+
+/* =================================== APP_VINYL (src/app_vinyl.h) ============================== */
+static float sd_capsule(v3 p, v3 a, v3 b, float r) {                              /* src/sdf.h:162-171 */
+    v3 ab = sub3(b, a);
+    float t = g_clamp(dot3(sub3(p, a), ab) / dot3(ab, ab), 0.0f, 1.0f);
+    return len3(sub3(add3(scale3(ab, t), a), p)) - r;
+}
+static inline m3 M3cols(v3 a, v3 b, v3 c) { m3 m; m.c0 = a; m.c1 = b; m.c2 = c; return m; }
+enum { VY_MAT_DEBUG = 0, VY_MAT_GROOVE, VY_MAT_DEAD_WAX, VY_MAT_LABEL, VY_MAT_LOGO, VY_MAT_SHINY };   /* :20-24 */
+typedef struct { m3 platter_rot; float time; } vinyl_state;                       /* _mutable platter_rot (:69) + u_time */
+
+static float vy_sdf_logo(v3 pos, float thick) {                                   /* :71-87 */
+    v3 b = V3(.25f, thick, 1.2f);
+    v3 d = V3(.7f, 0, 0);
+    v3 p = vec_mat(pos, rotate_around_y(30.0f));
+    float v1 = sd_box(sub3(p, d), b);
+    p = vec_mat(pos, rotate_around_y(-30.0f));
+    float v2 = sd_box(add3(p, d), b);
+    float x = sd_box(pos, V3(1.5f, thick, 1.35f));
+    float v = g_min(v1, v2);
+    return g_max(v, x);                                                           /* op_intersect, src/sdf.h:30-36 */
+}
+static v2 vy_sdf_platter(v3 p) {                                                  /* :89-128 */
+    const float thick = .1f;
+    v2 lead_in = V2(sd_y_cylinder(p, 6.0f, thick - .05f), (float)VY_MAT_DEAD_WAX);
+    v2 groove = V2(sd_y_cylinder(p, 5.9f, thick), (float)VY_MAT_GROOVE);
+    v2 dead_wax = V2(sd_y_cylinder(p, 3.0f, thick), (float)VY_MAT_DEAD_WAX);
+    v2 label = V2(sd_y_cylinder(p, 2.0f, thick), (float)VY_MAT_LABEL);
+    v2 logo = V2(vy_sdf_logo(p, thick - .0175f), (float)VY_MAT_LOGO);
+    float spc = sd_y_cylinder(p, .10f, .6f);
+    float sps = sd_sphere(sub3(p, V3(0, .3f, 0)), .10f);
+    v2 spindle = V2(g_min(spc, sps), (float)VY_MAT_SHINY);
+    v2 d0 = op_add2(groove, lead_in);
+    v2 d1 = op_add2(d0, dead_wax);
+    v2 d2 = op_add2(label, logo);
+    v2 d3 = op_add2(d1, d2);
+    v2 d4 = op_add2(d3, spindle);
+    float defect1 = sd_sphere(add3(p, V3(6.05f, 0, 0)), .1f);                     /* notches that make the spin visible */
+    float defect2 = sd_sphere(add3(p, V3(-6.05f, 0, 0)), .1f);
+    float defect = g_min(defect1, defect2);
+    return V2(op_sub1(d4.x, defect), d4.y);
+}
+static v2 vy_sdf_tonearm(const vinyl_state* st, v3 pos) {                         /* :130-249 */
+    v3 base_p = V3(-7, 0, -5);
+    float platter = sd_y_cylinder(pos, 6.25f, 1.0f);
+    float base_0 = sd_y_cylinder(sub3(pos, base_p), 3.0f, .25f);
+    float base_1 = op_sub1(base_0, platter);
+    float base_2 = sd_y_cylinder(sub3(pos, base_p), 1.25f, 1.0f);
+    float base_12 = g_min(base_1, base_2);
+    v2 base_a = V2(base_12, (float)VY_MAT_SHINY);
+    v2 base_b = V2(sd_y_cylinder(sub3(pos, base_p), 0.5f, 2.5f), (float)VY_MAT_SHINY);
+    v2 base = op_add2(base_a, base_b);
+
+    v3 p = vec_mat(pos, rotate_around_x(m_sin(st->time * 3.6758f) * .1f));        /* needle wobble */
+
+    const float R = .1f, H = .8f;
+    v3 a1 = V3(-6, H, -3), a11 = V3(-4.25f, H, 2), a2 = V3(-4.1f, H, 2.45f), a33 = V3(-3.5f, H, 3), a3 = V3(-2, H, 4);
+    float arm1 = sd_capsule(p, add3(base_p, V3(-1, H, -2)), a1, R);
+    float arm2 = sd_capsule(p, a1, a11, R);
+    float arm3 = sd_capsule(p, a33, a3, R);
+    v2 armb = sd_bezier(a11, a2, a33, p, R);
+    float arm_link1 = g_min(arm1, arm2);
+    float arm_link2 = g_min(arm_link1, arm3);
+    v2 arm = V2(g_min(arm_link2, armb.x), (float)VY_MAT_SHINY);
+
+    v3 arm_fwd = norm3(sub3(a3, a33));
+    v3 arm_up = V3(0, 1, 0);
+    v3 arm_right = cross3(arm_fwd, arm_up);
+    m3 arm_xform = M3cols(arm_fwd, arm_up, arm_right);
+
+    v3 clr_p = sub3(p, a3);                                                       /* collar */
+    float clr_r = R * 1.5f;
+    float collar = sd_cylinder(clr_p, V3(0, 0, 0), add3(V3(0, 0, 0), scale3(arm_fwd, .05f)), clr_r);
+
+    const float fl_w = .045f, fl_h = .020f;                                       /* finger lift */
+    float fl_len1 = clr_r * 1.0f;
+    float fl_len2 = fl_len1 * 1.2f;
+    m3 fl_rot = mat_mat(arm_xform, rotate_around_x(45.0f));
+    v3 fl_p = vec_mat(sub3(sub3(clr_p, scale3(arm_right, clr_r)), scale3(arm_up, clr_r)), fl_rot);
+    float fl1 = sd_box(fl_p, V3(fl_w, fl_h, fl_len1));
+    m3 fl_rot2 = rotate_around_x(-45.0f);
+    float fl2 = sd_box(sub3(vec_mat(sub3(fl_p, V3(0, 0, fl_len1)), fl_rot2), V3(0, 0, fl_len2)), V3(fl_w, fl_h, fl_len2));
+    float finger_lift = g_min(fl1, fl2);
+    v2 headshell = V2(g_min(collar, finger_lift), (float)VY_MAT_SHINY);
+
+    const float ctg_w = .05f, ctg_h = .05f;                                       /* cartridge */
+    float ctg_len1 = .3f, ctg_len2 = .5f;
+    v3 ctg_p = vec_mat(clr_p, arm_xform);
+    float ctg1 = sd_box(ctg_p, V3(ctg_len1, ctg_h, ctg_w));
+    m3 ctg_rot = rotate_around_z(44.0f);
+    v3 ctg2_p = sub3(vec_mat(sub3(ctg_p, V3(ctg_len1, 0, 0)), ctg_rot), V3(ctg_len2 - 0.03f, -.01f, 0));
+    float ctg2 = sd_box(ctg2_p, V3(ctg_len2, ctg_h, ctg_w));
+    float cut = sd_box(vec_mat(sub3(vec_mat(ctg2_p, rotate_around_x(10.0f)), V3(0, .05f, .175f)), rotate_around_y(-5.0f)),
+                       V3(ctg_len2 * 2.0f, ctg_h * 3.0f, ctg_w * 3.2f));
+    float cut2 = sd_box(vec_mat(sub3(ctg2_p, V3(.3f, .2f, 0)), rotate_around_z(10.0f)), V3(.4f, .2f, .3f));
+    float ctg12 = g_min(ctg1, ctg2);
+    float ctg12c = op_sub1(ctg12, cut);
+    v2 cartridge = V2(op_sub1(ctg12c, cut2), (float)VY_MAT_SHINY);
+
+    v2 tone1 = op_add2(base, arm);
+    v2 tone2 = op_add2(headshell, cartridge);
+    return op_add2(tone1, tone2);
+}
+static v2 vy_sdf(const vinyl_state* st, v3 pos) {                                 /* :251-259 */
+    v3 p = vec_mat(pos, st->platter_rot);
+    v2 plat = vy_sdf_platter(p);
+    v2 arm = vy_sdf_tonearm(st, pos);
+    return op_add2(plat, arm);
+}
+static v3 vy_sdf_normal(const vinyl_state* st, v3 p) {                            /* :261-272 */
+    const float dt = 0.001f;
+    v3 x = V3(dt, 0, 0), y = V3(0, dt, 0), z = V3(0, 0, dt);
+    return norm3(V3(vy_sdf(st, add3(p, x)).x - vy_sdf(st, sub3(p, x)).x,
+                    vy_sdf(st, add3(p, y)).x - vy_sdf(st, sub3(p, y)).x,
+                    vy_sdf(st, add3(p, z)).x - vy_sdf(st, sub3(p, z)).x));
+}
+static inline float vy_saw(float x) { return x - floorf(x); }                     /* :274-277 */
+static inline float vy_pulse(float x) { return vy_saw(x + .5f) - vy_saw(x); }     /* :279-282 */
+
+static v3 vy_illuminate(const vinyl_state* st, v3 sun_dir, v3 eye, hit_t* hit) {  /* :287-373 */
+    v3 L = sun_dir;
+    v3 V = norm3(sub3(eye, hit->origin));
+    v3 base_color = V3(0, 0, 0);                                                  /* get_material over setup_scene (:40-54) */
+    switch (hit->material_id) {
+        case VY_MAT_DEBUG: base_color = V3(1, 1, 1); break;
+        case VY_MAT_GROOVE: base_color = V3(.01f, .01f, .01f); break;
+        case VY_MAT_DEAD_WAX: base_color = V3(.05f, .05f, .05f); break;
+        case VY_MAT_LABEL: base_color = V3(.5f, .5f, .0f); break;
+        case VY_MAT_LOGO: base_color = V3(0, 0, .7f); break;
+        case VY_MAT_SHINY: base_color = V3(.7f, .7f, .7f); break;
+        default: break;
+    }
+    if (hit->material_id == VY_MAT_GROOVE || hit->material_id == VY_MAT_DEAD_WAX) {
+        /* Ward anisotropic highlight in the platter's rotating frame */
+        hit->origin = vec_mat(hit->origin, st->platter_rot);
+        L = vec_mat(L, st->platter_rot);
+        V = vec_mat(V, st->platter_rot);
+        float r = len3(hit->origin);
+        v3 B = divs3(hit->origin, r);
+        v3 N = V3(0, 1, 0);
+        if (hit->material_id == VY_MAT_GROOVE) {
+            float rr = r + .07575f * noise_iq(scale3(hit->origin, 2.456f));
+            float s = vy_pulse(rr * 24.0f);
+            if (s > 0.0f) {
+                N = norm3(add3(N, B));
+                N = reflect3(N, V3(0, 1, 0));
+            }
+        }
+        if (hit->material_id == VY_MAT_DEAD_WAX) {
+            float s = vy_saw(r * 4.0f);
+            N = norm3(add3(N, scale3(B, (float)(s > .9f))));
+        }
+        v3 T = cross3(B, N);
+        const float ro_diff = 1.0f, ro_spec = .0725f, a_x = .025f, a_y = .5f;
+        v3 H = norm3(add3(V, L));
+        float dotLN = dot3(L, N);
+        v3 diffuse = scale3(scale3(base_color, ro_diff / PI_F), g_max(0.0f, dotLN));
+        float spec_a = ro_spec / m_sqrt(dotLN * dot3(V, N));
+        float spec_b = 1.0f / (4.0f * PI_F * a_x * a_y);
+        float ht = dot3(H, T) / a_x;
+        float hb = dot3(H, B) / a_y;
+        float spec_c = -2.0f * (ht * ht + hb * hb) / (1.0f + dot3(H, N));
+        v3 specular = scale3(scale3(scale3(V3(1, 1, 1), spec_a), spec_b), m_exp(spec_c));
+        return add3(diffuse, specular);
+    }
+    hit->normal = vy_sdf_normal(st, hit->origin);
+    v3 diffuse = scale3(base_color, g_max(0.0f, dot3(L, hit->normal)));
+    v3 H = norm3(add3(V, L));
+    v3 specular = rscale3(m_pow(g_max(0.0f, dot3(H, hit->normal)), 50.0f), V3(1, 1, 1));
+    return add3(diffuse, specular);
+}
+static float vy_sdf_shadow(const vinyl_state* st, ray_t ray) {                     /* :375-400 */
+    const int steps = 20;
+    const float end = 5.0f, penumbra_factor = 16.0f, darkest = .05f;
+    float t = 0.0f, umbra = 1.0f;
+    for (int i = 0; i < steps; i++) {
+        v3 p = add3(ray.origin, scale3(ray.direction, t));
+        v2 d = vy_sdf(st, p);
+        if (t > end) break;
+        if (d.x < .005f) return darkest;
+        t += d.x;
+        umbra = g_min(umbra, penumbra_factor * d.x / t);
+    }
+    return umbra;
+}
+static v3 vy_render(const uniforms_t* u, ray_t ray, v3 point_cam) {               /* :405-455 */
+    (void)point_cam;
+    const int steps = 60;                                                         /* the __cplusplus branch, :411-416 */
+    const float end = 40.0f;
+    const v3 sun_dir = norm3(V3(-1, 4, -3));                                      /* :284-285 */
+    vinyl_state st;
+    st.time = u->time;
+    float rot = u->time * 200.0f;
+    st.platter_rot = mat_mat(rotate_around_y(rot), rotate_around_x(m_sin(u->time) * .1f));
+    float t = 0.0f;
+    for (int i = 0; i < steps; i++) {
+        v3 p = add3(ray.origin, scale3(ray.direction, t));
+        v2 d = vy_sdf(&st, p);
+        if (t > end) break;
+        if (d.x < .005f) {
+            hit_t h;
+            h.t = t;
+            h.material_id = (int)d.y;
+            h.normal = V3(0, 1, 0);
+            h.origin = p;
+            ray_t sh_ray;
+            sh_ray.origin = add3(p, scale3(sun_dir, 0.05f));
+            sh_ray.direction = sun_dir;
+            float sh = vy_sdf_shadow(&st, sh_ray);
+            return scale3(vy_illuminate(&st, sun_dir, ray.origin, &h), sh);
+        }
+        t += d.x;
+    }
+    return V3(1, 1, 1);                                                           /* background, :15-18 */
+}
+static void vinyl_pixel(const uniforms_t* u, float fx, float fy, float out[4]) {  /* setup_camera :56-67, FOV 1. */
+    main_image(u, vy_render, V3(0, 5.75f, 6.75f), V3(0, -2.5f, 0), 1.0f, fx, fy, out);
+}
+
 /* ======================================= frame driver ========================================= */
 typedef void (*pixel_fn)(const uniforms_t*, float, float, float[4]);
 typedef struct {
@@ -893,3 +1262,5 @@ ORACLE_ENTRY(clouds, clouds_pixel)
 ORACLE_ENTRY(atmosphere, atmosphere_pixel)
 ORACLE_ENTRY(planet, planet_pixel)
 ORACLE_ENTRY(raytracer, raytracer_pixel)
+ORACLE_ENTRY(sdf_ao, sdf_ao_pixel)
+ORACLE_ENTRY(vinyl, vinyl_pixel)

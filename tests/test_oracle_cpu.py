@@ -11,7 +11,7 @@ from oracle import loader
 from shaderbox_b200.abi import default_params, Shard
 from util import bits_equal, diff_report
 
-ORACLE_APPS = ("APP_EGG", "APP_CLOUDS", "APP_ATMOSPHERE", "APP_PLANET", "APP_RAYTRACER")
+ORACLE_APPS = ("APP_EGG", "APP_CLOUDS", "APP_ATMOSPHERE", "APP_PLANET", "APP_RAYTRACER", "APP_SDF_AO", "APP_VINYL")
 
 
 @pytest.mark.parametrize("case", [c for c in FRAME_CASES if c[0] in ORACLE_APPS], ids=frame_key)
@@ -39,6 +39,18 @@ def test_ref_ops_reproduce_golden(golden_ops):
         want = golden_ops[op + "/out"]
         got = loader.ref_eval_op(op, a, want.shape[1])
         assert bits_equal(got, want), op
+
+
+@pytest.mark.skipif(not loader.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("app,w,h,t,ov", [
+    ("APP_SDF_AO", 97, 41, 3.3, {}), ("APP_SDF_AO", 64, 64, 0.0, {"fog_density": 0.3, "fog_falloff": 0.2}),
+    ("APP_VINYL", 131, 77, 3.7, {}), ("APP_EGG", 90, 50, 6.5, {}), ("APP_RAYTRACER", 120, 67, 4.0, {"u_mouse": (300.0, 40.0, 0.0, 0.0)}),
+    ("APP_CLOUDS", 64, 36, 20.0, {"cld_march_steps": 50, "cld_coverage": 0.45, "sun_dir": (0.1, 0.2, -0.9)}),
+])
+def test_c_oracle_equals_reference_build_on_other_inputs(app, w, h, t, ov):
+    p = default_params(w, h, t, **ov)
+    got, want = loader.oracle_render(app, p), loader.ref_render(app, p)
+    assert bits_equal(got, want), diff_report(got, want)
 
 
 def test_oracle_is_thread_and_shard_invariant():
