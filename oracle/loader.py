@@ -109,6 +109,19 @@ def ref_bake_volume(size, z0=0, nz=None):
     return out
 
 
+def oracle_bake_volume(size, z0=0, nz=None):
+    """The same slices from the plain-C restatement (oracle/sbx_oracle.c)."""
+    nz = size - z0 if nz is None else nz
+    lib = _load(ORACLE_SO)
+    out = np.empty((nz, size, size, 4), dtype=np.float32)
+    lib.sbxoracle_bake_volume.restype = C.c_int
+    lib.sbxoracle_bake_volume.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    rc = lib.sbxoracle_bake_volume(int(size), int(z0), int(nz), out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("sbxoracle_bake_volume failed: %d" % rc)
+    return out
+
+
 def ref_dds_header(size):
     """The bytes ddsvolgen writes in front of the volume, built from the reference's vendored DDS.h."""
     lib = _load(REF_SO)

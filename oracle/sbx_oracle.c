@@ -1180,6 +1180,62 @@ static void vinyl_pixel(const uniforms_t* u, float fx, float fy, float out[4]) {
     main_image(u, vy_render, V3(0, 5.75f, 6.75f), V3(0, -2.5f, 0), 1.0f, fx, fy, out);
 }
 
+/* ============ the 3-D noise volume of util/ddsvolgen (src/noise_worley.h + src/fbm.h:8) ========= */
+static inline v3 fract3(v3 a) { return V3(g_fract(a.x), g_fract(a.y), g_fract(a.z)); }
+static inline v3 floor3(v3 a) { return V3(floorf(a.x), floorf(a.y), floorf(a.z)); }
+static v3 hash_w(v3 x) {                                                          /* src/noise_worley.h:5-17 */
+    v3 xx = V3(dot3(x, V3(127.1f, 311.7f, 74.7f)), dot3(x, V3(269.5f, 183.3f, 246.1f)), dot3(x, V3(113.5f, 271.9f, 124.6f)));
+    return fract3(V3(m_sin(xx.x) * 43758.5453123f, m_sin(xx.y) * 43758.5453123f, m_sin(xx.z) * 43758.5453123f));
+}
+static v3 noise_w(v3 pos, float domain_repeat) {                                  /* src/noise_worley.h:20-51 */
+    v3 x = scale3(pos, domain_repeat);
+    v3 p = floor3(x), f = fract3(x);
+    float id = 0.0f;
+    v2 res = V2(100.0f, 100.0f);
+    for (int k = -1; k <= 1; k++)
+        for (int j = -1; j <= 1; j++)
+            for (int i = -1; i <= 1; i++) {
+                v3 b = V3((float)i, (float)j, (float)k);
+                v3 pb = add3(p, b);
+                v3 cell = V3(g_mod(pb.x, domain_repeat), g_mod(pb.y, domain_repeat), g_mod(pb.z, domain_repeat));
+                v3 r = add3(sub3(b, f), hash_w(cell));
+                float d = dot3(r, r);
+                if (d < res.x) {
+                    id = dot3(add3(p, b), V3(1.0f, 57.0f, 113.0f));
+                    res = V2(d, res.x);
+                } else if (d < res.y) {
+                    res.y = d;
+                }
+            }
+    return V3(m_sqrt(res.x), m_sqrt(res.y), fabsf(id));
+}
+/* DECL_FBM_FUNC_TILE(fbm_worley_tile, 4, (1. - (noise_w(p, L).r + .25))) and fbm_dds (util/ddsvolgen/src/ddsvolgen.cpp:52-61) */
+static float fbm_dds(v3 pos) {
+    const float lacunarity = 2.0f, init_gain = 1.0f, gain = .5f;
+    float H = init_gain, L = lacunarity, t = 0.0f;
+    for (int i = 0; i < 4; i++) {
+        t += (1.0f - (noise_w(pos, L).x + .25f)) * H;
+        L *= lacunarity;
+        H *= gain;
+    }
+    return t;
+}
+/* slices [z0, z0 + nz) of the size^3 RGBA32F volume, x fastest (ddsvolgen.cpp:101-116) */
+int sbxoracle_bake_volume(int size, int z0, int nz, float* out) {
+    if (!out || size <= 0 || z0 < 0 || nz < 0 || z0 + nz > size) return SBX_ERR_INVALID;
+    float* ptr = out;
+    for (int z = z0; z < z0 + nz; z++)
+        for (int y = 0; y < size; y++)
+            for (int x = 0; x < size; x++) {
+                v3 pos = divs3(adds3(V3((float)x, (float)y, (float)z), .5f), (float)size);
+                *ptr++ = fbm_dds(pos);
+                *ptr++ = 0.0f;
+                *ptr++ = 0.0f;
+                *ptr++ = 0.0f;
+            }
+    return SBX_OK;
+}
+
 /* ======================================= frame driver ========================================= */
 typedef void (*pixel_fn)(const uniforms_t*, float, float, float[4]);
 typedef struct {

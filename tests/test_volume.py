@@ -36,6 +36,12 @@ def test_ref_volume_reproduces_golden(golden_volume):
     assert bits_equal(loader.ref_bake_volume(128, 77, 1), golden_volume["v128_z77"])
 
 
+def test_c_oracle_volume_reproduces_golden(golden_volume):
+    assert bits_equal(loader.oracle_bake_volume(16), golden_volume["v16"])
+    assert bits_equal(loader.oracle_bake_volume(128, 77, 1), golden_volume["v128_z77"])
+    assert bits_equal(loader.oracle_bake_volume(128, 0, 1), golden_volume["v128_z0"])
+
+
 @pytest.mark.gpu
 def test_baked_volume_matches_reference_golden(golden_volume):
     r = sbx.Renderer("APP_CLOUDS", device=0)
