@@ -182,3 +182,14 @@ def test_prebuilt_kernel_images_are_sm100a_and_present():
         path = os.path.join(img_dir, app + ".plugin.cubin")
         assert os.path.exists(path), path + " missing: run __graft_entry__.build()"
     assert os.path.exists(os.path.join(img_dir, "sbx_util.cubin"))
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/sbx.h compiles as strict C99 and a C program drives the device-free entry points through libsbx.so."""
+    exe = tmp_path / "abi_c99"
+    lib_dir = os.path.dirname(sbx.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "tests", "native", "abi_c99.c"),
+                    "-o", str(exe), "-L" + lib_dir, "-lsbx", "-Wl,-rpath," + lib_dir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert '"ok": true' in r.stdout
