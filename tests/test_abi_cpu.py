@@ -193,3 +193,19 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert '"ok": true' in r.stdout
+
+
+def test_example_host_of_the_integration_guide_builds(tmp_path):
+    """examples/sbx_app.cpp is the C++ host INTEGRATION.md shows; it must compile and link against the shipped header + library
+    (it needs a B200 to do anything: here it only has to refuse politely)."""
+    exe = tmp_path / "sbx_app"
+    lib_dir = os.path.dirname(sbx.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", "sbx_app.cpp"),
+                    "-I" + os.path.join(ROOT, "include"), "-o", str(exe), "-L" + lib_dir, "-lsbx", "-Wl,-rpath," + lib_dir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+    import torch
+
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(exe), "x.h", "APP_X", "8", "8", "1", str(tmp_path / "f%04d.ppm")], capture_output=True, text=True)
+        assert r.returncode == 1 and "sbx_create" in r.stderr
