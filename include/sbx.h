@@ -17,7 +17,9 @@
  *   - every entry point returns 0 (SBX_OK) or a negative sbx_status; no exceptions cross the ABI
  *   - frames are row-major float4 (R,G,B,A=1), row 0 is fragCoord.y = 0.5 (GL / shadertoy
  *     bottom-up convention, src/main.h:12), pixel centre fragCoord = (x+0.5, y+0.5)
- *   - a context is bound to ONE device; calls on one context are serialised by the caller
+ *   - a context is bound to ONE device; calls on one context are serialised by the caller, but launches may go to
+ *     any streams: per-context device state (math tables, the lattice-hash memo) is complete before the call that
+ *     builds it returns, and per-launch state (sequence times, completion counters) is per launch
  *   - there is NO CPU path: if no sm_100-class device / kernel image is available the calls fail
  */
 #ifndef SBX_H_
@@ -85,6 +87,8 @@ typedef struct sbx_timing {
     int   grid_blocks, block_threads, regs_per_thread, blocks_per_sm;
     int   zero_copy;     /* 1 if sbx_render_host stored straight into a pinned+mapped host frame */
     int   lanes_per_pixel; /* 1, or P for a cooperative image (P lanes share one pixel's march) */
+    int   tail_rows;       /* rows at the end of the launch marched with tail_lanes_per_pixel lanes (hybrid image), else 0 */
+    int   tail_lanes_per_pixel;
 } sbx_timing;
 
 typedef struct sbx_ctx sbx_ctx;
@@ -145,11 +149,34 @@ int sbx_render_host_rgba8(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sh
 int sbx_render_frame(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
                      float* dev_frame, void* stream);
 
+/* One GPU's part of a full frame, for hosts that split a frame over the GPUs of a box (the pixels are independent --
+ * src/main.h:6-53 reads nothing but uniforms -- so any partition is exact):
+ *   rows        interleaved row stripes, as above ({1,1,0} or zeroed = every row), and/or
+ *   tile_parts  > 1: of the 8-pixel-wide warp tiles of each tile row, this launch renders the columns tx with
+ *               (tx + first_row_of_tile / 4) % tile_parts == tile_part -- a checkerboard of tiles.  Every part then
+ *               holds the same share of EVERY row, so parts are balanced by construction whatever the scene's
+ *               vertical structure (APP_CLOUDS: the sky/horizon/cloud bands).
+ *   done_flag   NULL, or a device-visible 32-bit word (this GPU's memory, a peer GPU's -- typically next to the frame
+ *               the pixels go to -- or mapped host memory): the launch's last thread block stores done_value there,
+ *               with system-scope release ordering, after every pixel of the launch has been stored.  Wait for it
+ *               with sbx_stream_wait_flags (stream-ordered, no host involvement) or by reading it.
+ * sbx_render_frame_part is sbx_render_frame with this description; asynchronous on `stream`. */
+typedef struct sbx_frame_part {
+    sbx_shard rows;
+    int tile_parts, tile_part;
+    unsigned* done_flag;
+    unsigned done_value;
+} sbx_frame_part;
+int sbx_render_frame_part(sbx_ctx* ctx, const sbx_params* p, const sbx_frame_part* part, float* dev_frame, void* stream);
+/* Make `stream` wait (on the device, cuStreamWaitValue32) until each of the n flags at dev_flags is >= value. */
+int sbx_stream_wait_flags(sbx_ctx* ctx, const unsigned* dev_flags, int n, unsigned value, void* stream);
+
 /* A time sequence in ONE launch: frame k is rendered with u_time = times[k] (the animation loop of the
  * reference's hosts -- `iGlobalTime` advancing per presented frame, src/uniform_buffer.h:34 -- batched, so
  * small frames fill the GPU and the launch cost is paid once).  Output: n_frames consecutive frames (each
  * rows*width float4, same row order / sharding as sbx_render_device).  Each frame is bit-identical to the
- * one sbx_render_* produces for that u_time.  `times` is a HOST array of n_frames floats (1 <= n <= 65535). */
+ * one sbx_render_* produces for that u_time.  `times` is a HOST array of n_frames floats (1 <= n <= 65535); it is
+ * consumed before the call returns (copied to a pinned staging slot), and the device entry point is asynchronous. */
 int sbx_render_sequence_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
                                const float* times, int n_frames, float* dev_rgba, void* stream);
 int sbx_render_sequence_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard_or_null,
@@ -171,8 +198,41 @@ int sbx_frame_release(sbx_ctx* ctx, float* imported);
  * complete once every rank has synchronised its stream. */
 int sbx_host_frame_register(sbx_ctx* ctx, void* host, size_t bytes, float** dev_alias_out);
 int sbx_host_frame_unregister(sbx_ctx* ctx, void* host);
+/* Host frames the render kernel can store into directly: pinned, mapped into every CUDA context of the process
+ * (portable).  A frame from sbx_host_alloc passed to sbx_render_host[_rgba8] takes the zero-copy path (the kernel's
+ * pixel stores travel over PCIe while other pixels are still being computed); a malloc'd / std::vector frame takes
+ * the render-in-HBM + copy path.  This is the allocator a shaderbox host should use for its frame. */
+int sbx_host_alloc(sbx_ctx* ctx, size_t bytes, void** host_out);
+int sbx_host_free(sbx_ctx* ctx, void* host);
 /* Synchronous device->host read of a frame buffer (after ordering `stream`). */
 int sbx_frame_read(sbx_ctx* ctx, const float* dev, float* host, size_t bytes, void* stream);
+
+/* ---- one frame over several GPUs of the box, from ONE process -------------------------------------------------
+ * The reference's hosts are single programs with one render loop (hlsltoy's message loop,
+ * util/hlsltoy/src/hlsltoy.cpp:494-520; VML's SDL_app.cpp): a group gives such a program every GPU of the box
+ * behind one call per frame.  devices = NULL means GPUs 0 .. n_gpus-1; a device may be listed more than once (the
+ * parts then share that GPU -- useful to exercise the N-part path on a 1-GPU machine).  Each GPU renders a
+ * checkerboard of 8x4 warp tiles (sbx_frame_part) straight into the destination:
+ *   sbx_multi_render_device  the group's frame in the FIRST device's memory (peers store over NVLink); asynchronous:
+ *                            the frame is complete for work enqueued afterwards on sbx_multi_stream(), or after
+ *                            sbx_multi_sync().  *dev_frame_out stays owned by the group.
+ *   sbx_multi_render_host    synchronous.  A frame from sbx_host_alloc is written by every GPU over its own PCIe link
+ *                            (no gather, no copy); any other host frame is rendered on the device path and copied.
+ * Frames are bit-identical to sbx_render_host on one GPU.  sbx_multi_ctx(i) exposes the i-th per-GPU context
+ * (options, timing).  sbx_multi_last_timing: kernel_ms of each GPU's last launch (after a sync / host render). */
+typedef struct sbx_multi sbx_multi;
+int sbx_multi_create(const int* devices_or_null, int n_gpus, sbx_multi** out);
+void sbx_multi_destroy(sbx_multi* m);
+int sbx_multi_gpus(sbx_multi* m);
+sbx_ctx* sbx_multi_ctx(sbx_multi* m, int i);
+int sbx_multi_load_app(sbx_multi* m, const char* app_name, const char* variant);
+int sbx_multi_set_option(sbx_multi* m, const char* key, int value);
+int sbx_multi_render_device(sbx_multi* m, const sbx_params* p, float** dev_frame_out);
+int sbx_multi_render_host(sbx_multi* m, const sbx_params* p, float* host_rgba);
+void* sbx_multi_stream(sbx_multi* m);
+int sbx_multi_sync(sbx_multi* m);
+int sbx_multi_last_timing(sbx_multi* m, float* kernel_ms_per_gpu, int capacity);
+const char* sbx_multi_last_error(sbx_multi* m);
 
 /* Scatter a compacted shard (as produced above / received from a peer) into a full frame on the
  * device: the de-interleave step after the multi-GPU gather. */
@@ -189,7 +249,10 @@ int sbx_bake_noise_volume_device(sbx_ctx* ctx, int size, int z0, int nz, float* 
 int sbx_bake_noise_volume_host(sbx_ctx* ctx, int size, int z0, int nz, float* host_rgba);
 int sbx_dds_volume_header(int size, unsigned char* out, int capacity);
 
-/* Options: "use_hash_table" 0|1, "hash_table_log2" 9..22 (noise_iq memo table), "host_zero_copy" 0|1,
+/* Options: "tail_waves_x100" T (default 100) / "tail_max_waves_x100" M: with the default variant of an app that ships a
+ * hybrid image, a launch smaller than M/100 waves of resident warps marches its last T/100 waves' worth of rows with
+ * 4 lanes per pixel (the tail of the launch drains 4 times faster) and the rest with one; 0 = never.
+ * "use_hash_table" 0|1, "hash_table_log2" 9..22 (noise_iq memo table), "host_zero_copy" 0|1,
  * "coop_waves_x100" W (default 250): with the default variant, launches smaller than W/100 waves of resident warps
  * use the app's 4-lanes-per-pixel cooperative image, launches smaller than 2W/100 waves the 2-lane one, if
  * shipped; 0 = never. */

@@ -58,7 +58,15 @@ class Timing(C.Structure):
         ("blocks_per_sm", C.c_int),
         ("zero_copy", C.c_int),
         ("lanes_per_pixel", C.c_int),
+        ("tail_rows", C.c_int),
+        ("tail_lanes_per_pixel", C.c_int),
     ]
+
+
+class FramePart(C.Structure):
+    """sbx_frame_part: one GPU's part of a full frame (row stripes and/or a checkerboard of warp tiles) + completion flag."""
+
+    _fields_ = [("rows", Shard), ("tile_parts", C.c_int), ("tile_part", C.c_int), ("done_flag", C.c_void_p), ("done_value", C.c_uint)]
 
 
 def default_params(width, height, u_time=0.0, **overrides):
@@ -86,6 +94,16 @@ def default_params(width, height, u_time=0.0, **overrides):
         else:
             setattr(p, k, v)
     return p
+
+
+def tile_part_mask(width, height, tile_parts, tile_part):
+    """Boolean [height, width] mask of the pixels a tile part renders; twin of the kernel's mapping (sbx_kernel.cuh):
+    the 8-pixel-wide tile column tx of a tile whose first row is r belongs to part (tx + r // 4) % tile_parts --
+    for 8x4 tiles and for the one-row tiles of a hybrid launch's tail alike, pixel (x, y) belongs to
+    part (x // 8 + y // 4) % tile_parts."""
+    import numpy as np
+
+    return (np.arange(width)[None, :] // 8 + np.arange(height)[:, None] // 4) % tile_parts == tile_part
 
 
 def shard_rows(stripe_rows, n_parts, part, height):

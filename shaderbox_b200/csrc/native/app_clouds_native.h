@@ -245,8 +245,17 @@ template <bool BOUNDED> SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-20
     return vec4(radiance, radiance, radiance, alpha * smoothstep(.0f, .2f, cutoff));
 }
 
+// lanes per pixel of the cooperative march compiled into this image: every warp (-DSBX_LANES_PER_PIXEL=P), or the
+// warps of the second region of a hybrid image (-DSBX_HYBRID_LANES=P, sbx_kernel.cuh); 1 = none
 #if SBX_LANES_PER_PIXEL > 1
-// Cooperative march (image built with -DSBX_LANES_PER_PIXEL=P): the P lanes of a pixel take the
+#define SBX_COOP_LANES SBX_LANES_PER_PIXEL
+#elif SBX_HYBRID_LANES > 1
+#define SBX_COOP_LANES SBX_HYBRID_LANES
+#else
+#define SBX_COOP_LANES 1
+#endif
+#if SBX_COOP_LANES > 1
+// Cooperative march (image built with -DSBX_LANES_PER_PIXEL=P or -DSBX_HYBRID_LANES=P): the P lanes of a pixel take the
 // view-march steps i = r*P + phase of round r.  Everything expensive in a step -- its density,
 // its Beer-Lambert factor T_i and its light march -- depends only on the step's position, not on
 // the accumulators, so the lanes evaluate P steps of the SAME ray at once; the accumulators
@@ -257,7 +266,7 @@ template <bool BOUNDED> SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-20
 // GPUs is ~2 waves of warps) no longer end in a long single-warp tail, and the lanes of a warp
 // sit on neighbouring steps of the same rays, which keeps their branches and table lines together.
 template <bool BOUNDED> SBX_FN vec4 render_clouds_coop(_in(ray_t) eye, bool active) {
-    const int P = SBX_LANES_PER_PIXEL;
+    const int P = SBX_COOP_LANES;
     const int lane = threadIdx.x & 31, phase = lane % P, base = lane - phase;
     const vec3 projection = eye.direction / eye.direction.y;
     vec3 origin = eye.origin + projection * 150.0f;
@@ -366,15 +375,21 @@ SBX_FN vec3 render(_in(ray_t) eye_ray, _in(vec3) point_cam) {   // :204-218
     const vec3 sky = render_sky_color(eye_ray.direction);
     sbx_kmax = 0u;
     const bool bounded = abs(sigma_scattering * (cld_thick / float(cld_march_steps))) < 80.0f;   // see sbx_beer_lambert
-#if SBX_LANES_PER_PIXEL > 1
-    const bool below = dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f;
-    // (the uniforms, hence `bounded`, are the same in every lane: the whole warp takes one instantiation)
-    vec4 cld = bounded ? render_clouds_coop<true>(eye_ray, !below) : render_clouds_coop<false>(eye_ray, !below);
-    if (below) return sky;
-#else
-    if (dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f) return sky;
-    vec4 cld = bounded ? render_clouds<true>(eye_ray) : render_clouds<false>(eye_ray);
+    vec4 cld;
+#if SBX_COOP_LANES > 1
+    if (sbx_coop) {   // warp-uniform (a compile-time constant unless the image is a hybrid)
+        const bool below = dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f;
+        // (the uniforms, hence `bounded`, are the same in every lane: the whole warp takes one instantiation)
+        cld = bounded ? render_clouds_coop<true>(eye_ray, !below) : render_clouds_coop<false>(eye_ray, !below);
+        if (below) return sky;
+    } else
 #endif
+    {
+#if SBX_LANES_PER_PIXEL == 1
+        if (dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f) return sky;
+        cld = bounded ? render_clouds<true>(eye_ray) : render_clouds<false>(eye_ray);
+#endif
+    }
     if (sbx_kmax >= (unsigned)sbx_L->hash_span) {                       // table miss: redo the pixel
         const float4 g = sbx_generic_pixel(sbx_L, eye_ray.origin.x, eye_ray.origin.y, eye_ray.origin.z,
                                            eye_ray.direction.x, eye_ray.direction.y, eye_ray.direction.z);

@@ -4,7 +4,7 @@
 //
 //   sbx_cli compile <app_header.h> <APP_NAME> <out.cubin>      (needs no GPU)
 //   sbx_cli render  <APP_NAME> <width> <height> <u_time> <out.rgba32f> [--variant native|plugin]
-//                   [--steps N] [--frames K] [--device D] [--ppm out.ppm] [--rgba8 out.rgba8]
+//                   [--steps N] [--frames K] [--device D] [--gpus N] [--ppm out.ppm] [--rgba8 out.rgba8]
 //   sbx_cli flatten <file.h>                                   (needs no GPU)
 //   sbx_cli bake <size> <out.dds> [--device D]                 (util/ddsvolgen: the 3-D noise texture, DDS + DX10 header + RGBA32F voxels)
 // `render` prints one JSON line with the kernel time of the last frame.  --ppm / --rgba8 render the
@@ -50,7 +50,7 @@ static int usage() {
     fprintf(stderr,
             "usage: sbx_cli compile <app_header.h> <APP_NAME> <out.cubin>\n"
             "       sbx_cli render <APP_NAME> <width> <height> <u_time> <out.rgba32f|-> [--variant v] [--steps n] "
-            "[--frames k] [--device d] [--ppm out.ppm] [--rgba8 out.rgba8]\n"
+            "[--frames k] [--device d] [--gpus n] [--ppm out.ppm] [--rgba8 out.rgba8]\n"
             "       sbx_cli flatten <file.h>\n"
             "       sbx_cli bake <size> <out.dds> [--device d]\n");
     return 2;
@@ -110,36 +110,53 @@ int main(int argc, char** argv) {
         const char* variant = nullptr;
         const char* ppm_path = nullptr;
         const char* rgba8_path = nullptr;
-        int steps = 0, frames = 1, device = 0;
+        int steps = 0, frames = 1, device = 0, gpus = 1;
         for (int i = 7; i + 1 < argc; i += 2) {
             if (!strcmp(argv[i], "--variant")) variant = argv[i + 1];
             else if (!strcmp(argv[i], "--steps")) steps = atoi(argv[i + 1]);
             else if (!strcmp(argv[i], "--frames")) frames = atoi(argv[i + 1]);
             else if (!strcmp(argv[i], "--device")) device = atoi(argv[i + 1]);
+            else if (!strcmp(argv[i], "--gpus")) gpus = atoi(argv[i + 1]);
             else if (!strcmp(argv[i], "--ppm")) ppm_path = argv[i + 1];
             else if (!strcmp(argv[i], "--rgba8")) rgba8_path = argv[i + 1];
             else return usage();
         }
-        sbx_ctx* ctx = nullptr;
-        int st = sbx_create(device, &ctx);
-        if (st != SBX_OK) { fprintf(stderr, "sbx_create: %s: %s\n", sbx_strerror(st), sbx_last_error(nullptr)); return 1; }
-        st = sbx_load_app(ctx, app, variant);
-        if (st != SBX_OK) { fprintf(stderr, "sbx_load_app: %s: %s\n", sbx_strerror(st), sbx_last_error(ctx)); return 1; }
         sbx_params p;
-        sbx_default_params(&p, w, h);
+        if (w <= 0 || h <= 0 || sbx_default_params(&p, w, h) != SBX_OK) { fprintf(stderr, "render: bad frame size %dx%d\n", w, h); return 2; }
         p.u_time = t;
         if (steps > 0) p.cld_march_steps = steps;
-        std::vector<float> frame((size_t)w * h * 4);
+        // one GPU: a context; several: a group (one process, one part of every frame per GPU, sbx_multi_*)
+        sbx_multi* group = nullptr;
+        sbx_ctx* ctx = nullptr;
+        int st;
+        if (gpus > 1) {
+            st = sbx_multi_create(nullptr, gpus, &group);
+            if (st != SBX_OK) { fprintf(stderr, "sbx_multi_create(%d): %s: %s\n", gpus, sbx_strerror(st), sbx_last_error(nullptr)); return 1; }
+            st = sbx_multi_load_app(group, app, variant);
+            if (st != SBX_OK) { fprintf(stderr, "sbx_multi_load_app: %s: %s\n", sbx_strerror(st), sbx_multi_last_error(group)); return 1; }
+            ctx = sbx_multi_ctx(group, 0);
+        } else {
+            st = sbx_create(device, &ctx);
+            if (st != SBX_OK) { fprintf(stderr, "sbx_create: %s: %s\n", sbx_strerror(st), sbx_last_error(nullptr)); return 1; }
+            st = sbx_load_app(ctx, app, variant);
+            if (st != SBX_OK) { fprintf(stderr, "sbx_load_app: %s: %s\n", sbx_strerror(st), sbx_last_error(ctx)); return 1; }
+        }
+        // the frame lives in pinned + mapped host memory: the render kernels store into it directly
+        void* frame_mem = nullptr;
+        const size_t frame_floats = (size_t)w * h * 4;
+        st = sbx_host_alloc(ctx, frame_floats * sizeof(float), &frame_mem);
+        if (st != SBX_OK) { fprintf(stderr, "sbx_host_alloc: %s: %s\n", sbx_strerror(st), sbx_last_error(ctx)); return 1; }
+        float* frame = (float*)frame_mem;
         sbx_timing tm{};
         for (int f = 0; f < frames; ++f) {
-            st = sbx_render_host(ctx, &p, nullptr, frame.data());
-            if (st != SBX_OK) { fprintf(stderr, "sbx_render_host: %s: %s\n", sbx_strerror(st), sbx_last_error(ctx)); return 1; }
+            st = group ? sbx_multi_render_host(group, &p, frame) : sbx_render_host(ctx, &p, nullptr, frame);
+            if (st != SBX_OK) { fprintf(stderr, "render: %s: %s\n", sbx_strerror(st), group ? sbx_multi_last_error(group) : sbx_last_error(ctx)); return 1; }
             sbx_last_timing(ctx, &tm);
         }
         if (strcmp(out_path, "-")) {
             FILE* fp = fopen(out_path, "wb");
             if (!fp) { perror(out_path); return 1; }
-            fwrite(frame.data(), sizeof(float), frame.size(), fp);
+            fwrite(frame, sizeof(float), frame_floats, fp);
             fclose(fp);
         }
         if (ppm_path || rgba8_path) {
@@ -165,11 +182,12 @@ int main(int argc, char** argv) {
                 fclose(fp);
             }
         }
-        printf("{\"app\": \"%s\", \"width\": %d, \"height\": %d, \"u_time\": %g, \"kernel_ms\": %.4f, \"d2h_ms\": %.4f, "
+        printf("{\"app\": \"%s\", \"width\": %d, \"height\": %d, \"u_time\": %g, \"gpus\": %d, \"kernel_ms\": %.4f, \"d2h_ms\": %.4f, "
                "\"mpix_per_s\": %.2f, \"grid\": %d, \"block\": %d, \"regs\": %d, \"ctas_per_sm\": %d}\n",
-               app, w, h, t, tm.kernel_ms, tm.d2h_ms, tm.kernel_ms > 0 ? (double)w * h / tm.kernel_ms * 1e-3 : 0.0,
+               app, w, h, t, gpus > 1 ? gpus : 1, tm.kernel_ms, tm.d2h_ms, tm.kernel_ms > 0 ? (double)w * h / tm.kernel_ms * 1e-3 : 0.0,
                tm.grid_blocks, tm.block_threads, tm.regs_per_thread, tm.blocks_per_sm);
-        sbx_destroy(ctx);
+        sbx_host_free(ctx, frame_mem);
+        if (group) sbx_multi_destroy(group); else sbx_destroy(ctx);
         return 0;
     }
     return usage();

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -27,51 +28,14 @@
 
 namespace {
 
-// ---- lazily bound driver API ------------------------------------------------------------------
-struct driver_api {
-    void* lib = nullptr;
-    CUresult (*Init)(unsigned);
-    CUresult (*DeviceGet)(CUdevice*, int);
-    CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice);
-    CUresult (*DevicePrimaryCtxRetain)(CUcontext*, CUdevice);
-    CUresult (*DevicePrimaryCtxRelease)(CUdevice);
-    CUresult (*CtxPushCurrent)(CUcontext);
-    CUresult (*CtxPopCurrent)(CUcontext*);
-    CUresult (*ModuleLoadData)(CUmodule*, const void*);
-    CUresult (*ModuleUnload)(CUmodule);
-    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
-    CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*);
-    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction);
-    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
-    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t);
-    CUresult (*MemAlloc)(CUdeviceptr*, size_t);
-    CUresult (*MemFree)(CUdeviceptr);
-    CUresult (*MemcpyHtoD)(CUdeviceptr, const void*, size_t);
-    CUresult (*MemcpyDtoH)(void*, CUdeviceptr, size_t);
-    CUresult (*MemcpyDtoHAsync)(void*, CUdeviceptr, size_t, CUstream);
-    CUresult (*MemcpyHtoDAsync)(CUdeviceptr, const void*, size_t, CUstream);
-    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
-                             CUstream, void**, void**);
-    CUresult (*StreamSynchronize)(CUstream);
-    CUresult (*EventCreate)(CUevent*, unsigned);
-    CUresult (*EventRecord)(CUevent, CUstream);
-    CUresult (*EventSynchronize)(CUevent);
-    CUresult (*EventElapsedTime)(float*, CUevent, CUevent);
-    CUresult (*EventDestroy)(CUevent);
-    CUresult (*GetErrorString)(CUresult, const char**);
-    CUresult (*PointerGetAttribute)(void*, CUpointer_attribute, CUdeviceptr);
-    CUresult (*MemHostRegister)(void*, size_t, unsigned);
-    CUresult (*MemHostUnregister)(void*);
-    CUresult (*MemHostGetDevicePointer)(CUdeviceptr*, void*, unsigned);
-    CUresult (*IpcGetMemHandle)(CUipcMemHandle*, CUdeviceptr);
-    CUresult (*IpcOpenMemHandle)(CUdeviceptr*, CUipcMemHandle, unsigned);
-    CUresult (*IpcCloseMemHandle)(CUdeviceptr);
-};
+using sbx::driver_api;
 
 std::mutex g_mutex;
 std::string g_last_error;   // for calls without a context
 
-driver_api* load_driver(std::string* err) {
+}  // namespace
+
+sbx::driver_api* sbx::load_driver(std::string* err) {
     static driver_api api;
     std::lock_guard<std::mutex> lock(g_mutex);
     if (api.lib) return &api;
@@ -119,10 +83,25 @@ driver_api* load_driver(std::string* err) {
     SBX_SYM(IpcGetMemHandle, "cuIpcGetMemHandle")
     SBX_SYM(IpcOpenMemHandle, "cuIpcOpenMemHandle_v2")
     SBX_SYM(IpcCloseMemHandle, "cuIpcCloseMemHandle")
+    SBX_SYM(MemsetD32, "cuMemsetD32_v2")
+    SBX_SYM(MemHostAlloc, "cuMemHostAlloc")
+    SBX_SYM(MemFreeHost, "cuMemFreeHost")
+    SBX_SYM(StreamWaitValue32, "cuStreamWaitValue32_v2")
+    SBX_SYM(StreamWaitEvent, "cuStreamWaitEvent")
+    SBX_SYM(StreamCreate, "cuStreamCreate")
+    SBX_SYM(StreamDestroy, "cuStreamDestroy_v2")
+    SBX_SYM(MemAllocAsync, "cuMemAllocAsync")
+    SBX_SYM(MemFreeAsync, "cuMemFreeAsync")
+    SBX_SYM(DeviceGetCount, "cuDeviceGetCount")
+    SBX_SYM(DeviceCanAccessPeer, "cuDeviceCanAccessPeer")
+    SBX_SYM(CtxEnablePeerAccess, "cuCtxEnablePeerAccess")
 #undef SBX_SYM
     api.lib = lib;
     return &api;
 }
+
+namespace {
+using sbx::load_driver;
 
 struct kernel_image {
     CUmodule module = nullptr;
@@ -130,6 +109,7 @@ struct kernel_image {
     int regs = 0, max_threads = 0, blocks_per_sm = 0;
     int warps_per_cta = 4;
     int tile_w = SBX_TILE_W, tile_h = SBX_TILE_H, lanes_per_pixel = 1;   // sbx_image_info of the image
+    int hybrid_lanes = 0;         // > 1: the image has a second region marched with this many lanes per pixel
     std::string variant;
 };
 
@@ -157,6 +137,7 @@ struct sbx_ctx {
     kernel_image* current = nullptr;
     kernel_image* current_coop = nullptr;   // cooperative images of the same app (4 and 2 lanes per pixel), for small grids
     kernel_image* current_coop2 = nullptr;
+    kernel_image* current_hybrid = nullptr; // one lane per pixel first, the tail of the launch with 4 lanes per pixel
     std::string current_app;
 
     CUmodule util_module = nullptr;
@@ -169,9 +150,17 @@ struct sbx_ctx {
     int opt_use_hash = 1;
     int opt_zero_copy = 1;        // sbx_render_host: store straight into pinned+mapped host frames
     int opt_coop_waves_x100 = 250;   // use the cooperative image when the grid is below this many waves of resident warps
+    int opt_tail_waves_x100 = 100;   // hybrid image: march the last this-many waves of the launch with several lanes per pixel
+    int opt_tail_max_waves_x100 = 1200;  // ... for launches below this many waves (a long launch amortises its tail anyway)
+    CUdeviceptr done_counters = 0;   // ring of CTA counters for launches that signal a completion flag
+    unsigned done_seq = 0;
 
-    CUdeviceptr times = 0;        // u_time values of a sequence launch
-    int times_cap = 0;
+    // u_time values of sequence launches travel through a small ring of pinned staging slots (so the copy is truly
+    // asynchronous and the caller's array is consumed before the call returns); the device copy is stream-ordered
+    static const int kTimeSlots = 8, kTimeSlotFloats = 65536;
+    float* times_ring = nullptr;  // kTimeSlots * kTimeSlotFloats pinned floats
+    CUevent times_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned times_seq = 0;
     CUdeviceptr frame = 0;        // internal frame for sbx_render_host
     size_t frame_bytes = 0;
     CUevent ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -192,6 +181,8 @@ struct sbx_ctx {
         return fail(SBX_ERR_CUDA, "%s: %s (%d)", what, s ? s : "?", (int)r);
     }
 };
+
+CUcontext sbx::context_of(sbx_ctx* ctx) { return ctx ? ctx->ctx : nullptr; }
 
 namespace {
 
@@ -245,6 +236,8 @@ int ensure_tables(sbx_ctx* ctx, CUstream stream, bool force_table = false) {
             SBX_TRY(ctx->cu->LaunchKernel(ctx->k_hash, (unsigned)((len + 255) / 256), 1, 1, 256, 1, 1,
                                           SBX_LUT_MATH_BYTES, stream, args, nullptr),
                     "launch sbx_hash_table_kernel");
+            // the table is per-context state shared by every later launch on ANY stream: finish it here, once
+            SBX_TRY(ctx->cu->StreamSynchronize(stream), "cuStreamSynchronize(hash table)");
             ctx->hash_lo = lo;
             ctx->hash_len = len;
             ctx->timing.launches += 1;
@@ -269,7 +262,7 @@ int bind_image(sbx_ctx* ctx, const std::string& key, const std::string& cubin, c
         int v[4] = {0, 0, 0, 0};
         if (ctx->cu->ModuleGetGlobal(&info, &bytes, img.module, "sbx_image_info") == CUDA_SUCCESS && bytes >= sizeof v &&
             ctx->cu->MemcpyDtoH(v, info, sizeof v) == CUDA_SUCCESS && v[0] > 0 && v[1] > 0 && v[2] > 0) {
-            img.tile_w = v[0]; img.tile_h = v[1]; img.lanes_per_pixel = v[2];
+            img.tile_w = v[0]; img.tile_h = v[1]; img.lanes_per_pixel = v[2]; img.hybrid_lanes = v[3] > 1 ? v[3] : 0;
         }
     }
     auto it = ctx->images.find(key);
@@ -280,6 +273,7 @@ int bind_image(sbx_ctx* ctx, const std::string& key, const std::string& cubin, c
 
 bool valid_shard(const sbx_shard* s, sbx_shard* out) {
     sbx_shard r = {1, 1, 0};
+    if (s && s->n_parts < 0) return false;
     if (s && s->n_parts > 0) r = *s;
     if (r.stripe_rows <= 0) r.stripe_rows = 1;
     if (r.part < 0 || r.part >= r.n_parts) return false;
@@ -394,8 +388,10 @@ void sbx_destroy(sbx_ctx* ctx) {
         if (ctx->util_module) ctx->cu->ModuleUnload(ctx->util_module);
         if (ctx->lut) ctx->cu->MemFree(ctx->lut);
         if (ctx->hash_tab) ctx->cu->MemFree(ctx->hash_tab);
-        if (ctx->times) ctx->cu->MemFree(ctx->times);
+        if (ctx->times_ring) ctx->cu->MemFreeHost(ctx->times_ring);
+        for (CUevent e : ctx->times_ev) if (e) ctx->cu->EventDestroy(e);
         if (ctx->frame) ctx->cu->MemFree(ctx->frame);
+        if (ctx->done_counters) ctx->cu->MemFree(ctx->done_counters);
         if (ctx->ev0) ctx->cu->EventDestroy(ctx->ev0);
         if (ctx->ev1) ctx->cu->EventDestroy(ctx->ev1);
         if (ctx->ev2) ctx->cu->EventDestroy(ctx->ev2);
@@ -458,10 +454,11 @@ int sbx_load_app(sbx_ctx* ctx, const char* app_name, const char* variant) {
         ctx->current = &it->second;
         ctx->current_coop = nullptr;
         ctx->current_coop2 = nullptr;
+        ctx->current_hybrid = nullptr;
         ctx->current_app = app_name;
         if (!(variant && *variant) && v == "native") {
             // default selection only: the cooperative builds of the same scene kernel, if shipped
-            for (const char* cv : {"coop", "coop2"}) {
+            for (const char* cv : {"coop", "coop2", "hybrid"}) {
                 const std::string ckey = std::string(app_name) + "/" + cv;
                 auto ct = ctx->images.find(ckey);
                 if (ct == ctx->images.end()) {
@@ -470,7 +467,8 @@ int sbx_load_app(sbx_ctx* ctx, const char* app_name, const char* variant) {
                         bind_image(ctx, ckey, cbin, cv) == SBX_OK)
                         ct = ctx->images.find(ckey);
                 }
-                if (ct != ctx->images.end()) (std::strcmp(cv, "coop") ? ctx->current_coop2 : ctx->current_coop) = &ct->second;
+                if (ct != ctx->images.end())
+                    (!std::strcmp(cv, "coop") ? ctx->current_coop : !std::strcmp(cv, "coop2") ? ctx->current_coop2 : ctx->current_hybrid) = &ct->second;
             }
         }
         return SBX_OK;
@@ -495,15 +493,42 @@ int sbx_set_option(sbx_ctx* ctx, const char* key, int value) {
     if (!std::strcmp(key, "use_hash_table")) { ctx->opt_use_hash = value ? 1 : 0; return SBX_OK; }
     if (!std::strcmp(key, "host_zero_copy")) { ctx->opt_zero_copy = value ? 1 : 0; return SBX_OK; }
     if (!std::strcmp(key, "coop_waves_x100")) { if (value < 0) return SBX_ERR_INVALID; ctx->opt_coop_waves_x100 = value; return SBX_OK; }
+    if (!std::strcmp(key, "tail_waves_x100")) { if (value < 0) return SBX_ERR_INVALID; ctx->opt_tail_waves_x100 = value; return SBX_OK; }
+    if (!std::strcmp(key, "tail_max_waves_x100")) { if (value < 0) return SBX_ERR_INVALID; ctx->opt_tail_max_waves_x100 = value; return SBX_OK; }
     return SBX_ERR_INVALID;
 }
 
-static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_rgba, void* stream_,
-                         int out_is_frame, int out_rgba8 = 0, const float* dev_times = nullptr, int n_frames = 1) {
+// what one render launch covers and where it goes (the public entry points fill one of these)
+struct launch_job {
+    const sbx_shard* rows = nullptr;   // row stripes (NULL = every row)
+    int col_parts = 1, col_part = 0;   // tile-column interleave (frame outputs only)
+    int out_is_frame = 0, out_rgba8 = 0;
+    const float* dev_times = nullptr;  // sequence launch
+    int n_frames = 1;
+    unsigned* done_flag = nullptr;     // completion signal
+    unsigned done_value = 0;
+};
+
+static void plan_region(sbx_region* r, int width, int tile_w, int tile_h, int col_parts, int row0, int rows, int warps_per_cta) {
+    const int tiles_x = (width + tile_w - 1) / tile_w;
+    r->tiles_per_row = col_parts > 1 ? (tiles_x + col_parts - 1) / col_parts : tiles_x;
+    r->row0 = row0;
+    r->rows = rows;
+    r->warps = ((rows + tile_h - 1) / tile_h) * r->tiles_per_row;
+    // the grid is rounded up to whole CTAs: the largest warp index is < warps + warps_per_cta
+    const unsigned long long nmax = (unsigned long long)r->warps + (unsigned long long)warps_per_cta;
+    r->magic = (r->tiles_per_row > 0 && nmax * (unsigned long long)r->tiles_per_row < (1ull << 40))
+                   ? ((1ull << 40) + (unsigned long long)r->tiles_per_row - 1) / (unsigned long long)r->tiles_per_row : 0ull;
+}
+
+static int render_launch(sbx_ctx* ctx, const sbx_params* p, const launch_job& job, float* dev_rgba, void* stream_) {
     if (!ctx || !p || !dev_rgba || p->width <= 0 || p->height <= 0) return SBX_ERR_INVALID;
     if (!ctx->current) return ctx->fail(SBX_ERR_UNKNOWN_APP, "sbx_load_app was not called");
     sbx_shard s;
-    if (!valid_shard(shard, &s)) return ctx->fail(SBX_ERR_INVALID, "bad shard");
+    if (!valid_shard(job.rows, &s)) return ctx->fail(SBX_ERR_INVALID, "bad shard");
+    if (job.col_parts < 1 || job.col_part < 0 || job.col_part >= job.col_parts) return ctx->fail(SBX_ERR_INVALID, "bad tile shard");
+    if (job.col_parts > 1 && !job.out_is_frame) return ctx->fail(SBX_ERR_INVALID, "tile shards render into a full frame only");
+    const int n_frames = job.n_frames;
     CUstream stream = (CUstream)stream_;
     ctx_scope scope(ctx);
     ctx->timing.launches = 0;
@@ -517,36 +542,65 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
     L.n_parts = s.n_parts;
     L.part = s.part;
     L.local_rows = shard_rows(s, p->height);
-    if (L.local_rows == 0) return SBX_OK;
+    L.col_parts = job.col_parts;
+    L.col_part = job.col_part;
     kernel_image* img = ctx->current;
-    if (ctx->current_coop || ctx->current_coop2) {
+    int rows_tail = 0;   // rows of the launch marched by the hybrid image's second region
+    if (L.local_rows > 0 && (ctx->current_coop || ctx->current_coop2 || ctx->current_hybrid)) {
         // A frame (or one rank's share of it) that is only a few waves of resident warps ends in a long tail of single
-        // warps still marching; the cooperative images cut every ray into P shorter pieces (multi-GPU).
-        // Measured on one rank's share of CLOUDS 1080p (tools/shard_time.py): 2.3 waves -> P=4 wins, 4.6 -> P=2, 9 -> P=1.
-        const long long warps = (long long)((p->width + img->tile_w - 1) / img->tile_w) * ((L.local_rows + img->tile_h - 1) / img->tile_h) * n_frames;
+        // warps still marching.  The hybrid image marches the LAST rows of the launch (about one wave of warps) with 4
+        // lanes per pixel -- pieces 4 times shorter, which drain 4 times faster -- and everything before them with one
+        // lane per pixel, so only the tail pays the cooperative march's overhead (multi-GPU).  Without a
+        // hybrid image the whole launch switches to a cooperative image when it is small: measured on one rank's share
+        // of CLOUDS 1080p (tools/shard_time.py): 2.3 waves -> P=4 wins, 4.6 -> P=2, 9 -> P=1.
+        const int cols = job.col_parts > 1 ? job.col_parts : 1;
+        const long long tiles_x = ((p->width + img->tile_w - 1) / img->tile_w + cols - 1) / cols;
+        const long long warps = tiles_x * ((L.local_rows + img->tile_h - 1) / img->tile_h) * n_frames;
         const long long resident = (long long)ctx->sm_count * img->blocks_per_sm * img->warps_per_cta;
-        if (ctx->current_coop && warps * 100 < resident * ctx->opt_coop_waves_x100) img = ctx->current_coop;
+        if (ctx->current_hybrid && n_frames == 1 && ctx->opt_tail_waves_x100 > 0) {
+            if (warps * 100 < resident * ctx->opt_tail_max_waves_x100) {
+                // tail = opt_tail_waves waves of one-lane warps' worth of rows, in whole 8x4 tile rows
+                long long tail_warps = resident * ctx->opt_tail_waves_x100 / 100;
+                long long tile_rows = (tail_warps + tiles_x - 1) / tiles_x;
+                rows_tail = (int)std::min<long long>((long long)L.local_rows, tile_rows * SBX_TILE_H);
+                if (L.local_rows - rows_tail < SBX_TILE_H) rows_tail = L.local_rows;
+                rows_tail = L.local_rows - ((L.local_rows - rows_tail) / SBX_TILE_H) * SBX_TILE_H;   // region 0 is whole tile rows
+                img = ctx->current_hybrid;
+            }
+        } else if (ctx->current_coop && warps * 100 < resident * ctx->opt_coop_waves_x100) img = ctx->current_coop;
         else if (ctx->current_coop2 && warps * 100 < resident * ctx->opt_coop_waves_x100 * 2) img = ctx->current_coop2;
     }
-    L.tiles_x = (p->width + img->tile_w - 1) / img->tile_w;
-    L.tiles_y = (L.local_rows + img->tile_h - 1) / img->tile_h;
+    // the tile checkerboard is defined on 8-pixel columns: every image with 8-wide tiles (one lane per pixel, 4 lanes,
+    // hybrid) cuts the same parts; the 2-lane image (16-wide tiles) would not
+    if (job.col_parts > 1 && img->tile_w != SBX_TILE_W) { img = ctx->current; rows_tail = 0; }
+    if (L.local_rows > 0) {
+        plan_region(&L.reg[0], p->width, img->tile_w, img->tile_h, job.col_parts, 0, L.local_rows - rows_tail, img->warps_per_cta);
+        if (rows_tail > 0)
+            plan_region(&L.reg[1], p->width, 32 / img->hybrid_lanes, 1, job.col_parts, L.local_rows - rows_tail, rows_tail, img->warps_per_cta);
+    }
     L.out = dev_rgba;
-    L.out_is_frame = out_is_frame;
-    L.out_rgba8 = out_rgba8;
-    L.times = dev_times;
+    L.out_is_frame = job.out_is_frame;
+    L.out_rgba8 = job.out_rgba8;
+    L.times = job.dev_times;
     L.hash_tab = (const float4*)ctx->hash_tab;
     L.hash_bias = SBX_HASH_MAGIC_BITS + ctx->hash_lo;
     L.hash_len = ctx->hash_len;
     L.hash_span = ctx->hash_len;
     L.lut = (const void*)ctx->lut;
-
-    const long long tiles = (long long)L.tiles_x * L.tiles_y;
-    {   // the grid is rounded up to whole CTAs: the largest warp index is < tiles + warps_per_cta
-        const unsigned long long nmax = (unsigned long long)tiles + (unsigned long long)img->warps_per_cta;
-        L.tiles_x_magic = (nmax * (unsigned long long)L.tiles_x < (1ull << 40))
-                              ? ((1ull << 40) + (unsigned long long)L.tiles_x - 1) / (unsigned long long)L.tiles_x : 0ull;
+    if (job.done_flag) {
+        if (!ctx->done_counters) {
+            SBX_TRY(ctx->cu->MemAlloc(&ctx->done_counters, 64 * sizeof(unsigned)), "cuMemAlloc(done counters)");
+            SBX_TRY(ctx->cu->MemsetD32(ctx->done_counters, 0u, 64), "cuMemsetD32(done counters)");
+        }
+        L.done_counter = (unsigned*)(uintptr_t)(ctx->done_counters + (ctx->done_seq++ % 64u) * sizeof(unsigned));
+        L.done_flag = job.done_flag;
+        L.done_value = job.done_value;
     }
-    const unsigned grid = (unsigned)((tiles + img->warps_per_cta - 1) / img->warps_per_cta);
+
+    const long long warps = (long long)L.reg[0].warps + L.reg[1].warps;
+    // a launch without pixels still publishes its completion flag (one idle CTA)
+    if (warps == 0 && !job.done_flag) return SBX_OK;
+    const unsigned grid = (unsigned)std::max<long long>(1, (warps + img->warps_per_cta - 1) / img->warps_per_cta);
     void* args[] = {&L};
     SBX_TRY(ctx->cu->EventRecord(ctx->ev0, stream), "cuEventRecord");
     SBX_TRY(ctx->cu->LaunchKernel(img->render, grid, (unsigned)n_frames, 1, (unsigned)img->warps_per_cta * 32, 1, 1,
@@ -559,6 +613,8 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sha
     ctx->timing.regs_per_thread = img->regs;
     ctx->timing.blocks_per_sm = img->blocks_per_sm;
     ctx->timing.lanes_per_pixel = img->lanes_per_pixel;
+    ctx->timing.tail_rows = rows_tail;
+    ctx->timing.tail_lanes_per_pixel = rows_tail > 0 ? img->hybrid_lanes : 0;
     ctx->timing.kernel_ms = -1.0f;   // resolved lazily by sbx_last_timing
     ctx->timing.d2h_ms = 0.0f;
     return SBX_OK;
@@ -578,27 +634,43 @@ static CUdeviceptr mapped_host_alias(sbx_ctx* ctx, const void* host) {
 }
 
 int sbx_render_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_rgba, void* stream) {
-    return render_launch(ctx, p, shard, dev_rgba, stream, 0);
+    launch_job job;
+    job.rows = shard;
+    return render_launch(ctx, p, job, dev_rgba, stream);
 }
 
 int sbx_render_sequence_device(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, const float* times, int n_frames,
-                               float* dev_rgba, void* stream) {
+                               float* dev_rgba, void* stream_) {
     if (!ctx || !times || n_frames < 1 || n_frames > 65535) return SBX_ERR_INVALID;
+    CUstream stream = (CUstream)stream_;
+    CUdeviceptr dev_times = 0;
+    const size_t bytes = (size_t)n_frames * sizeof(float);
     {
         ctx_scope scope(ctx);
-        if (n_frames > ctx->times_cap) {
-            if (ctx->times) { ctx->cu->StreamSynchronize((CUstream)stream); ctx->cu->MemFree(ctx->times); }
-            ctx->times = 0;
-            ctx->times_cap = 0;
-            if (ctx->cu->MemAlloc(&ctx->times, (size_t)n_frames * sizeof(float)) != CUDA_SUCCESS)
-                return ctx->fail(SBX_ERR_NOMEM, "cuMemAlloc(times) failed");
-            ctx->times_cap = n_frames;
+        if (!ctx->times_ring) {
+            void* ring = nullptr;
+            if (ctx->cu->MemHostAlloc(&ring, (size_t)sbx_ctx::kTimeSlots * sbx_ctx::kTimeSlotFloats * sizeof(float), 0) != CUDA_SUCCESS)
+                return ctx->fail(SBX_ERR_NOMEM, "cuMemHostAlloc(times ring) failed");
+            ctx->times_ring = (float*)ring;
+            for (CUevent& e : ctx->times_ev) SBX_TRY(ctx->cu->EventCreate(&e, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
         }
-        // stream-ordered after earlier launches that read the buffer; the host array is consumed before returning
-        SBX_TRY(ctx->cu->MemcpyHtoDAsync(ctx->times, times, (size_t)n_frames * sizeof(float), (CUstream)stream), "cuMemcpyHtoDAsync(times)");
-        SBX_TRY(ctx->cu->StreamSynchronize((CUstream)stream), "cuStreamSynchronize");
+        // the slot is free once the copy that last used it has run (8 sequence launches ago: normally long done)
+        const unsigned slot = ctx->times_seq++ % (unsigned)sbx_ctx::kTimeSlots;
+        if (ctx->times_seq > (unsigned)sbx_ctx::kTimeSlots) SBX_TRY(ctx->cu->EventSynchronize(ctx->times_ev[slot]), "cuEventSynchronize(times slot)");
+        float* staged = ctx->times_ring + (size_t)slot * sbx_ctx::kTimeSlotFloats;
+        std::memcpy(staged, times, bytes);          // the caller's array is consumed here
+        SBX_TRY(ctx->cu->MemAllocAsync(&dev_times, bytes, stream), "cuMemAllocAsync(times)");
+        SBX_TRY(ctx->cu->MemcpyHtoDAsync(dev_times, staged, bytes, stream), "cuMemcpyHtoDAsync(times)");
+        SBX_TRY(ctx->cu->EventRecord(ctx->times_ev[slot], stream), "cuEventRecord(times slot)");
     }
-    return render_launch(ctx, p, shard, dev_rgba, stream, 0, 0, (const float*)(uintptr_t)ctx->times, n_frames);
+    launch_job job;
+    job.rows = shard;
+    job.dev_times = (const float*)(uintptr_t)dev_times;
+    job.n_frames = n_frames;
+    const int st = render_launch(ctx, p, job, dev_rgba, stream_);
+    ctx_scope scope(ctx);
+    ctx->cu->MemFreeAsync(dev_times, stream);       // stream-ordered: after the kernel that reads it
+    return st;
 }
 
 int sbx_render_sequence_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, const float* times, int n_frames,
@@ -633,7 +705,51 @@ int sbx_render_sequence_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard*
 }
 
 int sbx_render_frame(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, float* dev_frame, void* stream) {
-    return render_launch(ctx, p, shard, dev_frame, stream, 1);
+    launch_job job;
+    job.rows = shard;
+    job.out_is_frame = 1;
+    return render_launch(ctx, p, job, dev_frame, stream);
+}
+
+int sbx_render_frame_part(sbx_ctx* ctx, const sbx_params* p, const sbx_frame_part* part, float* dev_frame, void* stream) {
+    if (!part) return SBX_ERR_INVALID;
+    launch_job job;
+    job.out_is_frame = 1;
+    sbx_shard rows = part->rows;
+    job.rows = &rows;
+    job.col_parts = part->tile_parts > 1 ? part->tile_parts : 1;
+    job.col_part = part->tile_parts > 1 ? part->tile_part : 0;
+    if (part->tile_parts > 1 && (part->tile_part < 0 || part->tile_part >= part->tile_parts))
+        return ctx ? ctx->fail(SBX_ERR_INVALID, "bad tile part") : SBX_ERR_INVALID;
+    job.done_flag = part->done_flag;
+    job.done_value = part->done_value;
+    return render_launch(ctx, p, job, dev_frame, stream);
+}
+
+int sbx_stream_wait_flags(sbx_ctx* ctx, const unsigned* dev_flags, int n, unsigned value, void* stream) {
+    if (!ctx || !dev_flags || n < 0) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    for (int i = 0; i < n; ++i)
+        SBX_TRY(ctx->cu->StreamWaitValue32((CUstream)stream, (CUdeviceptr)(uintptr_t)(dev_flags + i), value, CU_STREAM_WAIT_VALUE_GEQ),
+                "cuStreamWaitValue32");
+    return SBX_OK;
+}
+
+int sbx_host_alloc(sbx_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out || bytes == 0) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    void* h = nullptr;
+    if (ctx->cu->MemHostAlloc(&h, bytes, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP) != CUDA_SUCCESS)
+        return ctx->fail(SBX_ERR_NOMEM, "cuMemHostAlloc(%zu) failed", bytes);
+    *out = h;
+    return SBX_OK;
+}
+
+int sbx_host_free(sbx_ctx* ctx, void* host) {
+    if (!ctx || !host) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    SBX_TRY(ctx->cu->MemFreeHost(host), "cuMemFreeHost");
+    return SBX_OK;
 }
 
 int sbx_frame_alloc(sbx_ctx* ctx, size_t bytes, float** out) {
@@ -641,6 +757,7 @@ int sbx_frame_alloc(sbx_ctx* ctx, size_t bytes, float** out) {
     ctx_scope scope(ctx);
     CUdeviceptr d = 0;
     if (ctx->cu->MemAlloc(&d, bytes) != CUDA_SUCCESS) return ctx->fail(SBX_ERR_NOMEM, "cuMemAlloc(%zu) failed", bytes);
+    if ((bytes & 3u) == 0) ctx->cu->MemsetD32(d, 0u, bytes / 4);   // frames (and completion flags kept behind them) start zeroed
     *out = (float*)(uintptr_t)d;
     return SBX_OK;
 }
@@ -731,7 +848,10 @@ static int render_host(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard
             ctx->frame_bytes = bytes;
         }
     }
-    int st = render_launch(ctx, p, &s, (float*)(alias ? alias : ctx->frame), nullptr, 0, rgba8);
+    launch_job job;
+    job.rows = &s;
+    job.out_rgba8 = rgba8;
+    int st = render_launch(ctx, p, job, (float*)(alias ? alias : ctx->frame), nullptr);
     if (st != SBX_OK) return st;
     ctx_scope scope(ctx);
     if (!alias) SBX_TRY(ctx->cu->MemcpyDtoHAsync(host, ctx->frame, bytes, nullptr), "cuMemcpyDtoHAsync");
@@ -753,7 +873,10 @@ int sbx_render_host_rgba8(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* sh
 
 int sbx_render_device_rgba8(sbx_ctx* ctx, const sbx_params* p, const sbx_shard* shard, unsigned char* dev_rgba8, void* stream) {
     if (((uintptr_t)dev_rgba8 & 3u) != 0) return ctx ? ctx->fail(SBX_ERR_INVALID, "rgba8 frame must be 4-byte aligned") : SBX_ERR_INVALID;
-    return render_launch(ctx, p, shard, (float*)dev_rgba8, stream, 0, 1);
+    launch_job job;
+    job.rows = shard;
+    job.out_rgba8 = 1;
+    return render_launch(ctx, p, job, (float*)dev_rgba8, stream);
 }
 
 int sbx_unshard_device(sbx_ctx* ctx, int width, int height, const sbx_shard* shard, const float* dev_part,

@@ -4,9 +4,67 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+
 #include "../../include/sbx.h"
 
 namespace sbx {
+// ---- lazily bound driver API (dlopen: the library loads, and exports its symbols, on a machine without a driver)
+struct driver_api {
+    void* lib = nullptr;
+    CUresult (*Init)(unsigned);
+    CUresult (*DeviceGet)(CUdevice*, int);
+    CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice);
+    CUresult (*DevicePrimaryCtxRetain)(CUcontext*, CUdevice);
+    CUresult (*DevicePrimaryCtxRelease)(CUdevice);
+    CUresult (*CtxPushCurrent)(CUcontext);
+    CUresult (*CtxPopCurrent)(CUcontext*);
+    CUresult (*ModuleLoadData)(CUmodule*, const void*);
+    CUresult (*ModuleUnload)(CUmodule);
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
+    CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*);
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction);
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t);
+    CUresult (*MemAlloc)(CUdeviceptr*, size_t);
+    CUresult (*MemFree)(CUdeviceptr);
+    CUresult (*MemcpyHtoD)(CUdeviceptr, const void*, size_t);
+    CUresult (*MemcpyDtoH)(void*, CUdeviceptr, size_t);
+    CUresult (*MemcpyDtoHAsync)(void*, CUdeviceptr, size_t, CUstream);
+    CUresult (*MemcpyHtoDAsync)(CUdeviceptr, const void*, size_t, CUstream);
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             CUstream, void**, void**);
+    CUresult (*StreamSynchronize)(CUstream);
+    CUresult (*EventCreate)(CUevent*, unsigned);
+    CUresult (*EventRecord)(CUevent, CUstream);
+    CUresult (*EventSynchronize)(CUevent);
+    CUresult (*EventElapsedTime)(float*, CUevent, CUevent);
+    CUresult (*EventDestroy)(CUevent);
+    CUresult (*GetErrorString)(CUresult, const char**);
+    CUresult (*PointerGetAttribute)(void*, CUpointer_attribute, CUdeviceptr);
+    CUresult (*MemHostRegister)(void*, size_t, unsigned);
+    CUresult (*MemHostUnregister)(void*);
+    CUresult (*MemHostGetDevicePointer)(CUdeviceptr*, void*, unsigned);
+    CUresult (*IpcGetMemHandle)(CUipcMemHandle*, CUdeviceptr);
+    CUresult (*IpcOpenMemHandle)(CUdeviceptr*, CUipcMemHandle, unsigned);
+    CUresult (*IpcCloseMemHandle)(CUdeviceptr);
+    CUresult (*MemsetD32)(CUdeviceptr, unsigned, size_t);
+    CUresult (*MemHostAlloc)(void**, size_t, unsigned);
+    CUresult (*MemFreeHost)(void*);
+    CUresult (*StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned);
+    CUresult (*StreamWaitEvent)(CUstream, CUevent, unsigned);
+    CUresult (*StreamCreate)(CUstream*, unsigned);
+    CUresult (*StreamDestroy)(CUstream);
+    CUresult (*MemAllocAsync)(CUdeviceptr*, size_t, CUstream);
+    CUresult (*MemFreeAsync)(CUdeviceptr, CUstream);
+    CUresult (*DeviceGetCount)(int*);
+    CUresult (*DeviceCanAccessPeer)(int*, CUdevice, CUdevice);
+    CUresult (*CtxEnablePeerAccess)(CUcontext, unsigned);
+};
+
+driver_api* load_driver(std::string* err);   // NULL + *err when libcuda is missing
+CUcontext context_of(sbx_ctx* ctx);          // the primary context a sbx_ctx is bound to
+
 std::string suffix_float_literals(const std::string& src);
 std::string library_dir();
 // NVRTC-compile an unchanged app header to an sm_100a cubin.  0 or SBX_ERR_*; log gets the compiler output.

@@ -13,7 +13,7 @@ import os
 
 import numpy as np
 
-from .abi import Params, Shard, Timing, default_params, shard_rows, SBX_OK
+from .abi import FramePart, Params, Shard, Timing, default_params, shard_rows, SBX_OK
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsbx.so")
@@ -54,6 +54,26 @@ def lib():
         L.sbx_render_sequence_device.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.sbx_render_sequence_host.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_int, C.c_void_p]
         L.sbx_render_frame.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_void_p]
+        L.sbx_render_frame_part.argtypes = [C.c_void_p, P(Params), P(FramePart), C.c_void_p, C.c_void_p]
+        L.sbx_stream_wait_flags.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_void_p]
+        L.sbx_host_alloc.argtypes = [C.c_void_p, C.c_size_t, P(C.c_void_p)]
+        L.sbx_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.sbx_multi_create.argtypes = [P(C.c_int), C.c_int, P(C.c_void_p)]
+        L.sbx_multi_destroy.argtypes = [C.c_void_p]
+        L.sbx_multi_destroy.restype = None
+        L.sbx_multi_gpus.argtypes = [C.c_void_p]
+        L.sbx_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+        L.sbx_multi_ctx.restype = C.c_void_p
+        L.sbx_multi_load_app.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.sbx_multi_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.sbx_multi_render_device.argtypes = [C.c_void_p, P(Params), P(C.c_void_p)]
+        L.sbx_multi_render_host.argtypes = [C.c_void_p, P(Params), C.c_void_p]
+        L.sbx_multi_stream.argtypes = [C.c_void_p]
+        L.sbx_multi_stream.restype = C.c_void_p
+        L.sbx_multi_sync.argtypes = [C.c_void_p]
+        L.sbx_multi_last_timing.argtypes = [C.c_void_p, P(C.c_float), C.c_int]
+        L.sbx_multi_last_error.argtypes = [C.c_void_p]
+        L.sbx_multi_last_error.restype = C.c_char_p
         L.sbx_frame_alloc.argtypes = [C.c_void_p, C.c_size_t, P(C.c_void_p)]
         L.sbx_frame_free.argtypes = [C.c_void_p, C.c_void_p]
         L.sbx_frame_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
@@ -81,6 +101,10 @@ EXPORTS = (
     "sbx_render_host_rgba8", "sbx_render_device_rgba8", "sbx_render_sequence_device", "sbx_render_sequence_host",
     "sbx_host_frame_register", "sbx_host_frame_unregister",
     "sbx_bake_noise_volume_device", "sbx_bake_noise_volume_host", "sbx_dds_volume_header",
+    "sbx_render_frame_part", "sbx_stream_wait_flags", "sbx_host_alloc", "sbx_host_free",
+    "sbx_multi_create", "sbx_multi_destroy", "sbx_multi_gpus", "sbx_multi_ctx", "sbx_multi_load_app", "sbx_multi_set_option",
+    "sbx_multi_render_device", "sbx_multi_render_host", "sbx_multi_stream", "sbx_multi_sync", "sbx_multi_last_timing",
+    "sbx_multi_last_error",
 )
 
 
@@ -204,6 +228,28 @@ class Renderer:
         self._check(self._L.sbx_render_frame(self._ctx, C.byref(params), C.byref(sh), C.c_void_p(dev_frame_ptr),
                                              C.c_void_p(stream)), "sbx_render_frame")
 
+    def render_frame_part(self, params, dev_frame_ptr, shard=None, tile_parts=1, tile_part=0, done_flag=0, done_value=0, stream=0):
+        """This GPU's part of a full frame (row stripes and/or a checkerboard of warp tiles) straight into the frame at
+        `dev_frame_ptr`; the launch's last thread block stores `done_value` at `done_flag` (device-visible address)."""
+        part = FramePart(Shard(*shard) if shard is not None else Shard(1, 1, 0), int(tile_parts), int(tile_part),
+                         C.c_void_p(done_flag or None), int(done_value))
+        self._check(self._L.sbx_render_frame_part(self._ctx, C.byref(params), C.byref(part), C.c_void_p(dev_frame_ptr),
+                                                  C.c_void_p(stream)), "sbx_render_frame_part")
+
+    def stream_wait_flags(self, dev_flags_ptr, n, value, stream=0):
+        """Stream-ordered wait (on the device) until each of the n 32-bit flags at `dev_flags_ptr` is >= value."""
+        self._check(self._L.sbx_stream_wait_flags(self._ctx, C.c_void_p(dev_flags_ptr), int(n), int(value), C.c_void_p(stream)),
+                    "sbx_stream_wait_flags")
+
+    def host_alloc(self, nbytes):
+        """A pinned + mapped host frame (sbx_host_alloc): sbx_render_host stores into it directly from the kernel."""
+        out = C.c_void_p()
+        self._check(self._L.sbx_host_alloc(self._ctx, nbytes, C.byref(out)), "sbx_host_alloc")
+        return out.value
+
+    def host_free(self, ptr):
+        self._check(self._L.sbx_host_free(self._ctx, C.c_void_p(ptr)), "sbx_host_free")
+
     def frame_alloc(self, nbytes):
         out = C.c_void_p()
         self._check(self._L.sbx_frame_alloc(self._ctx, nbytes, C.byref(out)), "sbx_frame_alloc")
@@ -278,3 +324,78 @@ class Renderer:
         self._check(self._L.sbx_eval_op(self._ctx, op.encode(), a.ctypes.data_as(C.c_void_p), a.shape[1],
                                         out.ctypes.data_as(C.c_void_p), out_width, a.shape[0]), "sbx_eval_op")
         return out
+
+
+class MultiRenderer:
+    """One frame over several GPUs from THIS process (sbx_multi_*): every GPU renders a checkerboard of warp tiles of
+    the frame straight into the destination.  `devices` may repeat a device (the parts then share it)."""
+
+    def __init__(self, app, devices=None, n_gpus=None, variant=None):
+        self._L = lib()
+        self._m = C.c_void_p()
+        if devices is None:
+            devices = list(range(int(n_gpus or 1)))
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        rc = self._L.sbx_multi_create(arr, len(self.devices), C.byref(self._m))
+        if rc != SBX_OK:
+            raise SbxError(rc, "sbx_multi_create", (self._L.sbx_last_error(None) or b"").decode(errors="replace"))
+        self._check(self._L.sbx_multi_load_app(self._m, app.encode(), variant.encode() if variant else None), "sbx_multi_load_app")
+        self.app = app
+
+    def _check(self, rc, where):
+        if rc != SBX_OK:
+            raise SbxError(rc, where, (self._L.sbx_multi_last_error(self._m) or b"").decode(errors="replace"))
+
+    def set_option(self, key, value):
+        self._check(self._L.sbx_multi_set_option(self._m, key.encode(), int(value)), "sbx_multi_set_option")
+
+    def close(self):
+        if self._m:
+            self._L.sbx_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def host_alloc(self, nbytes):
+        out = C.c_void_p()
+        self._check(self._L.sbx_host_alloc(self._L.sbx_multi_ctx(self._m, 0), nbytes, C.byref(out)), "sbx_host_alloc")
+        return out.value
+
+    def host_free(self, ptr):
+        self._check(self._L.sbx_host_free(self._L.sbx_multi_ctx(self._m, 0), C.c_void_p(ptr)), "sbx_host_free")
+
+    def render(self, width, height, u_time=0.0, out=None, **uniforms):
+        """Render to host memory (pageable numpy frame: assembled on the first GPU, then copied)."""
+        p = uniforms.pop("params", None) or default_params(width, height, u_time, **uniforms)
+        if out is None:
+            out = np.empty((p.height, p.width, 4), dtype=np.float32)
+        self._check(self._L.sbx_multi_render_host(self._m, C.byref(p), out.ctypes.data_as(C.c_void_p)), "sbx_multi_render_host")
+        return out
+
+    def render_host_ptr(self, params, host_ptr):
+        """Render into the host frame at `host_ptr`; zero-copy over every GPU's own PCIe link if it is pinned + mapped."""
+        self._check(self._L.sbx_multi_render_host(self._m, C.byref(params), C.c_void_p(host_ptr)), "sbx_multi_render_host")
+
+    def render_device(self, params):
+        """Enqueue one frame into the group's frame on the first GPU; returns its device pointer (valid after sync(), or
+        for work enqueued on stream())."""
+        out = C.c_void_p()
+        self._check(self._L.sbx_multi_render_device(self._m, C.byref(params), C.byref(out)), "sbx_multi_render_device")
+        return out.value
+
+    def stream(self):
+        return self._L.sbx_multi_stream(self._m)
+
+    def sync(self):
+        self._check(self._L.sbx_multi_sync(self._m), "sbx_multi_sync")
+
+    def kernel_ms(self):
+        n = len(self.devices)
+        arr = (C.c_float * n)()
+        self._check(self._L.sbx_multi_last_timing(self._m, arr, n), "sbx_multi_last_timing")
+        return [float(x) for x in arr]

@@ -33,6 +33,12 @@
 #ifndef SBX_LANES_PER_PIXEL
 #define SBX_LANES_PER_PIXEL 1
 #endif
+#ifndef SBX_HYBRID_LANES
+#define SBX_HYBRID_LANES 1
+#endif
+#if SBX_HYBRID_LANES > 1 && SBX_LANES_PER_PIXEL > 1
+#error "a hybrid image marches its first region with one lane per pixel"
+#endif
 #if SBX_LANES_PER_PIXEL == 1
 #define SBX_IMG_TILE_W SBX_TILE_W
 #define SBX_IMG_TILE_H SBX_TILE_H
@@ -40,8 +46,10 @@
 #define SBX_IMG_TILE_W (32 / SBX_LANES_PER_PIXEL)
 #define SBX_IMG_TILE_H 1
 #endif
-// read by the host at load time (cuModuleGetGlobal): { tile width, tile height, lanes per pixel, 0 }
-extern "C" __device__ const int sbx_image_info[4] = {SBX_IMG_TILE_W, SBX_IMG_TILE_H, SBX_LANES_PER_PIXEL, 0};
+// read by the host at load time (cuModuleGetGlobal): { tile width, tile height, lanes per pixel, lanes per pixel of the
+// second region of a hybrid image (0 = not hybrid) }
+extern "C" __device__ const int sbx_image_info[4] = {SBX_IMG_TILE_W, SBX_IMG_TILE_H, SBX_LANES_PER_PIXEL,
+                                                     SBX_HYBRID_LANES > 1 ? SBX_HYBRID_LANES : 0};
 
 // ---- TMA bulk copy of the LUT block: global -> shared, completion on an mbarrier --------------
 __device__ __forceinline__ unsigned sbx_smem_addr(const void* p) {
@@ -92,54 +100,98 @@ struct sbx_app {
     vec2 iResolution;
     float iGlobalTime;
     vec4 iMouse;
+    bool sbx_coop;                          // this warp marches with several lanes per pixel (warp-uniform)
 
 #include SBX_APP_HEADER
 
-    __device__ __forceinline__ explicit sbx_app(const sbx_launch* L)
+    __device__ __forceinline__ explicit sbx_app(const sbx_launch* L, bool coop = false)
         : sbx_L(L),
           iResolution(float(L->p.width), float(L->p.height)),
           iGlobalTime(sbx_param_time(L)),
-          iMouse(sbx_param_mouse(L)) {}
+          iMouse(sbx_param_mouse(L)),
+          sbx_coop(coop) {}
 };
 
 }  // namespace sbx_glsl
+
+// The last CTA to finish publishes done_value at done_flag (own HBM, a peer GPU's, or mapped host memory).  Every
+// thread's pixel stores are ordered before the CTA barrier; thread 0's system-scope fence is cumulative over them;
+// the counter hands "all CTAs have fenced" to the last one, which fences again before the flag store, so whoever
+// acquires the flag (cuStreamWaitValue32, a polling kernel, a host read) sees every pixel of this launch.
+__device__ __forceinline__ void sbx_signal_done(const sbx_launch& L) {
+    if (L.done_flag == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned ctas = gridDim.x * gridDim.y;
+        if (atomicAdd(L.done_counter, 1u) + 1u == ctas) {
+            *reinterpret_cast<volatile unsigned*>(L.done_counter) = 0u;   // ready for the next launch on this stream
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(L.done_flag), "r"(L.done_value) : "memory");
+        }
+    }
+}
 
 extern "C" __global__ void __launch_bounds__(SBX_WARPS_PER_CTA * 32, SBX_MIN_CTAS_PER_SM)
 sbx_render(const __grid_constant__ sbx_launch L) {
     sbx_stage_lut(L.lut);
 
-    const int warp = blockIdx.x * SBX_WARPS_PER_CTA + (threadIdx.x >> 5);
+    int warp = blockIdx.x * SBX_WARPS_PER_CTA + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    // warp -> (tile_x, tile_y): division by the host's magic number (exact for warp * tiles_x < 2^40, else 0 = divide)
-    const int tile_y = L.tiles_x_magic ? (int)(((unsigned long long)(unsigned)warp * L.tiles_x_magic) >> 40) : warp / L.tiles_x;
-    const int tile_x = warp - tile_y * L.tiles_x;
-#if SBX_LANES_PER_PIXEL == 1
-    const int x = tile_x * SBX_TILE_W + (lane & (SBX_TILE_W - 1));
-    const int lr = tile_y * SBX_TILE_H + (lane / SBX_TILE_W);
-    if (x >= L.p.width || lr >= L.local_rows) return;
-    const bool stores = true;
+#if SBX_HYBRID_LANES > 1
+    // hybrid image: the first reg[0].warps warps render 8x4 tiles with one lane per pixel, the warps after them
+    // render the remaining (upper) rows with SBX_HYBRID_LANES lanes per pixel -- the tail of the launch is cut
+    // into pieces P times shorter, so it drains P times faster, and only the tail pays the cooperative overhead
+    const bool coop = warp >= L.reg[0].warps;
+    if (coop) warp -= L.reg[0].warps;
+    const sbx_region& R = L.reg[coop ? 1 : 0];
+    const int P = coop ? SBX_HYBRID_LANES : 1;
 #else
-    // P lanes per pixel cooperate through warp shuffles, so every lane of the warp stays: lanes past
-    // the right edge (or in a tile past the last one) render the clamped pixel and store nothing
-    int x = tile_x * SBX_IMG_TILE_W + lane / SBX_LANES_PER_PIXEL;
-    int lr = tile_y;
-    const bool stores = x < L.p.width && lr < L.local_rows && (lane % SBX_LANES_PER_PIXEL) == 0;
-    x = x < L.p.width ? x : L.p.width - 1;
-    lr = lr < L.local_rows ? lr : L.local_rows - 1;
+    const bool coop = SBX_LANES_PER_PIXEL > 1;
+    const sbx_region& R = L.reg[0];
+    const int P = SBX_LANES_PER_PIXEL;
 #endif
-
-    // local (compacted) row -> frame row of this shard
-    const int y = L.n_parts == 1 ? lr : ((lr / L.stripe_rows) * L.n_parts + L.part) * L.stripe_rows + lr % L.stripe_rows;
-
-    sbx_glsl::sbx_app app(&L);
-    sbx_glsl::vec4 c;
-    app.mainImage(c, sbx_glsl::vec2(float(x) + 0.5f, float(y) + 0.5f));
-
-    if (stores) {
-        const size_t at = ((size_t)blockIdx.y * (size_t)L.local_rows + (size_t)(L.out_is_frame ? y : lr)) * (size_t)L.p.width + (size_t)x;
-        if (L.out_rgba8) __stcs(reinterpret_cast<unsigned*>(L.out) + at, sbx_pack_unorm8(c.x, c.y, c.z, c.w));
-        else __stcs(reinterpret_cast<float4*>(L.out) + at, make_float4(c.x, c.y, c.z, c.w));
+    const int tile_w = P == 1 ? SBX_TILE_W : 32 / P, tile_h = P == 1 ? SBX_TILE_H : 1;
+    // warp -> (tile row, column slot): division by the host's magic number (0 = divide)
+    const int trow = R.magic ? (int)(((unsigned long long)(unsigned)warp * R.magic) >> 40) : warp / R.tiles_per_row;
+    int tile_x = warp - trow * R.tiles_per_row;
+    const int lr0 = R.row0 + trow * tile_h;
+    if (L.col_parts > 1) {   // this part's columns of the row: (tile_x + lr0 / 4) % col_parts == col_part
+        int first = (L.col_part - (lr0 >> 2)) % L.col_parts;
+        first += first < 0 ? L.col_parts : 0;
+        tile_x = first + tile_x * L.col_parts;
     }
+    int x, lr;
+    bool valid;
+    if (P == 1) {
+        x = tile_x * SBX_TILE_W + (lane & (SBX_TILE_W - 1));
+        lr = lr0 + (lane / SBX_TILE_W);
+        valid = warp < R.warps && x < L.p.width && lr < R.row0 + R.rows;
+    } else {
+        // P lanes per pixel cooperate through warp shuffles, so every lane of the warp stays: lanes past
+        // the right edge (or in a tile past the last one) render the clamped pixel and store nothing
+        x = tile_x * tile_w + lane / P;
+        lr = lr0;
+        valid = warp < R.warps && x < L.p.width && lr < R.row0 + R.rows && (lane % P) == 0;
+        x = x < L.p.width ? x : L.p.width - 1;
+        lr = lr < L.local_rows ? lr : L.local_rows - 1;
+    }
+
+    if (valid || P > 1) {
+        // local (compacted) row -> frame row of this shard
+        const int y = L.n_parts == 1 ? lr : ((lr / L.stripe_rows) * L.n_parts + L.part) * L.stripe_rows + lr % L.stripe_rows;
+
+        sbx_glsl::sbx_app app(&L, coop);
+        sbx_glsl::vec4 c;
+        app.mainImage(c, sbx_glsl::vec2(float(x) + 0.5f, float(y) + 0.5f));
+
+        if (valid) {
+            const size_t at = ((size_t)blockIdx.y * (size_t)L.local_rows + (size_t)(L.out_is_frame ? y : lr)) * (size_t)L.p.width + (size_t)x;
+            if (L.out_rgba8) __stcs(reinterpret_cast<unsigned*>(L.out) + at, sbx_pack_unorm8(c.x, c.y, c.z, c.w));
+            else __stcs(reinterpret_cast<float4*>(L.out) + at, make_float4(c.x, c.y, c.z, c.w));
+        }
+    }
+    sbx_signal_done(L);
 }
 
 #endif  // SBX_KERNEL_CUH_

@@ -100,23 +100,36 @@ class _CudaArray:
 class SharedFrame:
     """The full frame on rank `dst`, mapped into every rank's address space with CUDA IPC
     (sbx_frame_alloc / sbx_frame_export / sbx_frame_import), so each rank's render kernel stores its
-    stripes straight into it over NVLink: the gather is fused into the render kernel."""
+    part straight into it over NVLink: the gather is fused into the render kernel.
+
+    Behind the frame sit `world` 32-bit completion flags (same allocation, so the same IPC mapping): the last thread
+    block of rank r's launch stores the frame number into flag r -- in rank `dst`'s memory, right behind its own pixel
+    stores on the same NVLink path -- and rank `dst`'s stream waits on the flags with cuStreamWaitValue32
+    (sbx_stream_wait_flags).  No collective and no host round trip sits between the last pixel and "frame complete".
+
+    split = "tiles": a checkerboard of 8x4 warp tiles dealt to the ranks (every rank renders the same share of EVERY
+    row: balanced by construction);  split = "rows": interleaved row stripes (include/sbx.h sbx_shard)."""
+
+    FLAG_BYTES = 4096
 
     def __init__(self, renderer, width, height, dst=0, group=None):
         self.renderer, self.width, self.height, self.dst, self.group = renderer, int(width), int(height), dst, group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.nbytes = self.width * self.height * 16
+        self.flags_offset = (self.nbytes + 255) // 256 * 256
         self.owner = self.rank == dst
+        self.epoch = 0
         handle = [None]
         if self.owner:
-            self.ptr = renderer.frame_alloc(self.nbytes)
+            self.ptr = renderer.frame_alloc(self.flags_offset + self.FLAG_BYTES)     # zero-filled: every flag starts at 0
             handle[0] = renderer.frame_export(self.ptr) if self.world > 1 else None
         if self.world > 1:
             dist.broadcast_object_list(handle, src=dst, group=group)
             if not self.owner:
                 self.ptr = renderer.frame_import(handle[0])
             dist.barrier(group)
+        self.flags_ptr = self.ptr + self.flags_offset
         dev = torch.device("cuda", renderer.device)
         self._done = torch.zeros(1, dtype=torch.float32, device=dev)
 
@@ -125,15 +138,41 @@ class SharedFrame:
         assert self.owner
         return torch.as_tensor(_CudaArray(self.ptr, (self.height, self.width, 4)), device=torch.device("cuda", self.renderer.device))
 
-    def render(self, params, stripe_rows=DEFAULT_STRIPE_ROWS):
-        """One frame: every rank launches its stripes into the shared frame, then a one-element all-reduce
-        on the same stream orders "all stripes have landed" before anything rank `dst` enqueues next."""
+    def part(self, split="tiles", stripe_rows=DEFAULT_STRIPE_ROWS):
+        """Keyword arguments of Renderer.render_frame_part for this rank's part of the frame."""
+        if split == "tiles":
+            return {"shard": None, "tile_parts": self.world, "tile_part": self.rank}
+        return {"shard": shard_of(self.rank, self.world, stripe_rows), "tile_parts": 1, "tile_part": 0}
+
+    def launch(self, params, split="tiles", stripe_rows=DEFAULT_STRIPE_ROWS, signal="flags", stream=None):
+        """Enqueue this rank's part of one frame (asynchronous).  With signal="flags" the launch publishes its
+        completion flag; complete() on the owner then orders "every part has landed" on its stream."""
         assert params.width == self.width and params.height == self.height
-        dev = torch.device("cuda", self.renderer.device)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        self.renderer.render_frame(params, self.ptr, shard=shard_of(self.rank, self.world, stripe_rows), stream=stream)
-        if self.world > 1:
+        if stream is None:
+            stream = torch.cuda.current_stream(torch.device("cuda", self.renderer.device)).cuda_stream
+        self.epoch += 1
+        flag = self.flags_ptr + 4 * self.rank if (signal == "flags" and self.world > 1) else 0
+        self.renderer.render_frame_part(params, self.ptr, done_flag=flag, done_value=self.epoch, stream=stream,
+                                        **self.part(split, stripe_rows))
+
+    def complete(self, signal="flags", stream=None):
+        if self.world == 1:
+            return
+        if signal == "flags":
+            if self.owner:
+                if stream is None:
+                    stream = torch.cuda.current_stream(torch.device("cuda", self.renderer.device)).cuda_stream
+                self.renderer.stream_wait_flags(self.flags_ptr, self.world, self.epoch, stream=stream)
+        else:
+            # a one-element all-reduce on the launching stream orders "every rank's kernel has finished"
             dist.all_reduce(self._done, group=self.group)
+
+    def render(self, params, stripe_rows=DEFAULT_STRIPE_ROWS, split="tiles", signal="flags"):
+        """One frame: every rank launches its part into the shared frame; on the owner, work enqueued after this call
+        on the current stream sees the complete frame.  (The other ranks do not wait: a caller that re-renders into
+        the same frame before the owner has consumed it needs its own ordering -- a barrier, or two frames.)"""
+        self.launch(params, split, stripe_rows, signal)
+        self.complete(signal)
 
     def close(self):
         if self.world > 1:
@@ -147,19 +186,20 @@ class SharedFrame:
 
 
 class SharedHostFrame:
-    """The full frame in HOST memory shared by the per-GPU processes of one box (a POSIX shared-memory file mapped by
-    every rank, pinned and device-mapped by sbx_host_frame_register): each rank's render kernel stores its stripes
-    straight into it over its own PCIe link.  This is the end-to-end path of an N-GPU host: no gather to one GPU, no
-    device->host copy of the assembled frame.
+    """The full frame in HOST memory shared by the per-GPU processes of one box (an anonymous shared-memory file
+    mapped by every rank, pinned and device-mapped by sbx_host_frame_register): each rank's render kernel stores its
+    part straight into it over its own PCIe link.  This is the end-to-end path of an N-GPU host: no gather to one
+    GPU, no device->host copy of the assembled frame.
 
-    Completion is a HOST-side barrier, in this order: every rank synchronises its own stream (its stores have then
-    landed in host memory), publishes the frame number in its slot of a control page behind the frame, and waits
-    until every slot shows it.  (A GPU-side collective after the kernel would not do: nothing orders one GPU's
-    PCIe writes to host memory before its NVLink traffic to another GPU.)"""
+    Completion: behind the frame sits a control page with one 32-bit slot per rank.  The last thread block of rank r's
+    launch stores the frame number into slot r (sbx_frame_part.done_flag: a system-scope release store issued after a
+    system-scope fence over the launch's pixel stores, travelling the same PCIe path behind them), and every rank's
+    host thread polls the slots until all show the frame number -- no stream synchronise, no collective."""
 
     def __init__(self, renderer, width, height, dst=0, group=None):
         import mmap
         import os
+        import tempfile
 
         import numpy as np
 
@@ -169,51 +209,58 @@ class SharedHostFrame:
         self.nbytes = self.width * self.height * 16
         page = mmap.PAGESIZE
         frame_bytes = (self.nbytes + page - 1) // page * page
-        size = frame_bytes + page                               # + one control page: int64 slot per rank
+        size = frame_bytes + page                               # + one control page: uint32 slot per rank
         name = [None]
+        fd = unlink = None
         if self.rank == dst:
-            base = "/dev/shm"
+            # anonymous shmem (memfd: no name in any directory, independent of the size of /dev/shm, gone with its last
+            # mapping); peers open it through /proc/<pid>/fd.  Fallback: an exclusive 0600 temp file in /dev/shm.
             try:
-                st = os.statvfs(base)
-                if st.f_bavail * st.f_frsize < size + (16 << 20):
-                    base = "/tmp"                               # a small /dev/shm (container default 64 MB): any file works
-            except OSError:
-                base = "/tmp"
-            name[0] = "%s/sbx_frame_%d_%d" % (base, os.getpid(), id(self) & 0xffff)
-            with open(name[0], "wb") as f:
-                f.truncate(size)
-        if self.world > 1:
-            dist.broadcast_object_list(name, src=dst, group=group)
-        self.path = name[0]
-        self._file = open(self.path, "r+b")
-        self._map = mmap.mmap(self._file.fileno(), size)
+                fd = os.memfd_create("sbx_frame")
+                os.ftruncate(fd, size)
+                name[0] = "/proc/%d/fd/%d" % (os.getpid(), fd)
+            except (AttributeError, OSError):
+                fd, unlink = tempfile.mkstemp(prefix="sbx_frame_", dir="/dev/shm")   # O_EXCL, mode 0600
+                os.ftruncate(fd, size)
+                name[0] = unlink
+        try:
+            if self.world > 1:
+                dist.broadcast_object_list(name, src=dst, group=group)
+            if self.rank != dst:
+                fd = os.open(name[0], os.O_RDWR)
+            self._map = mmap.mmap(fd, size)
+            if self.world > 1:
+                dist.barrier(group)                             # every rank holds its mapping: the name can go
+        finally:
+            if unlink is not None:
+                os.unlink(unlink)
+            if fd is not None:
+                os.close(fd)
         self.array = np.frombuffer(self._map, dtype=np.float32, count=self.width * self.height * 4).reshape(self.height, self.width, 4)
-        self._slots = np.frombuffer(self._map, dtype=np.int64, count=self.world, offset=frame_bytes)
+        self._slots = np.frombuffer(self._map, dtype=np.uint32, count=self.world, offset=frame_bytes)
         self._epoch = 0
-        self.timeout_s = 120.0                                  # a rank that died must not leave the others spinning forever
+        self.timeout_s = 20.0                                   # a rank that died must not leave the others spinning forever
         self.host_ptr = self.array.ctypes.data
-        self.alias = renderer.host_frame_register(self.host_ptr, frame_bytes)
+        self.alias = renderer.host_frame_register(self.host_ptr, size)
+        self.slots_alias = self.alias + frame_bytes
         if self.world > 1:
             dist.barrier(group)
-        if self.rank == dst:
-            os.unlink(self.path)          # every rank holds its mapping; the name is no longer needed
 
-    def render(self, params, stripe_rows=DEFAULT_STRIPE_ROWS):
+    def render(self, params, stripe_rows=DEFAULT_STRIPE_ROWS, split="tiles"):
         """One frame, synchronous: on return (every rank) the frame is complete in host memory (self.array)."""
         assert params.width == self.width and params.height == self.height
-        stream = torch.cuda.current_stream(torch.device("cuda", self.renderer.device)) if torch.cuda.is_available() else None
-        self.renderer.render_frame(params, self.alias, shard=shard_of(self.rank, self.world, stripe_rows),
-                                   stream=stream.cuda_stream if stream is not None else 0)
-        if stream is not None:
-            stream.synchronize()                                # this rank's stripes are in host memory
-        t_wait = time.monotonic()
+        stream = torch.cuda.current_stream(torch.device("cuda", self.renderer.device)).cuda_stream if torch.cuda.is_available() else 0
         self._epoch += 1
-        self._slots[self.rank] = self._epoch
+        part = ({"shard": None, "tile_parts": self.world, "tile_part": self.rank} if split == "tiles" else
+                {"shard": shard_of(self.rank, self.world, stripe_rows), "tile_parts": 1, "tile_part": 0})
+        self.renderer.render_frame_part(params, self.alias, done_flag=self.slots_alias + 4 * self.rank, done_value=self._epoch,
+                                        stream=stream, **part)
         slots, epoch = self._slots, self._epoch
+        t_wait = time.monotonic()
         spins = 0
-        while int(slots.min()) < epoch:                         # host barrier on the control page
+        while int(slots.min()) < epoch:                         # every rank's flag, written by its GPU
             spins += 1
-            if (spins & 0xfffff) == 0 and time.monotonic() - t_wait > self.timeout_s:
+            if (spins & 0xffff) == 0 and time.monotonic() - t_wait > self.timeout_s:
                 raise RuntimeError("SharedHostFrame: rank(s) %s did not finish frame %d within %.0f s"
                                    % ([r for r in range(self.world) if int(slots[r]) < epoch], epoch, self.timeout_s))
 
@@ -229,4 +276,3 @@ class SharedHostFrame:
             self._map.close()
         except BufferError:
             pass
-        self._file.close()

@@ -209,3 +209,17 @@ def test_example_host_of_the_integration_guide_builds(tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run([str(exe), "x.h", "APP_X", "8", "8", "1", str(tmp_path / "f%04d.ppm")], capture_output=True, text=True)
         assert r.returncode == 1 and "sbx_create" in r.stderr
+
+
+@pytest.mark.parametrize("w,h", [(8, 4), (331, 203), (1920, 1080), (7, 3)])
+def test_tile_parts_partition_every_frame(w, h):
+    """abi.tile_part_mask (twin of the kernel's tile checkerboard): the parts are disjoint, cover the frame, and every
+    part holds the same share of every tile row to within one tile."""
+    for parts in (1, 2, 3, 8):
+        total = np.zeros((h, w), int)
+        for part in range(parts):
+            m = abi.tile_part_mask(w, h, parts, part)
+            total += m
+            per_row = m.sum(axis=1)
+            assert per_row.max() - per_row.min() <= 8 and abs(per_row.mean() - w / parts) <= 8
+        assert (total == 1).all()

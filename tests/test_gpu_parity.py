@@ -299,31 +299,49 @@ def test_deterministic_run_to_run(renderers):
         assert bits_equal(a, r.render(320, 180, u_time=4.0))
 
 
-# ---- BASELINE.json configs at full size: size-independent properties -----------------------------
+# ---- BASELINE.json configs at full size ----------------------------------------------------------
+# (app, w, h, u_time, overrides, row step): every `step`-th row of the frame is compared; step 1 = the whole frame
 FULL = [
-    ("APP_CLOUDS", 1920, 1080, 1.5, {"cld_march_steps": 128}),
-    ("APP_ATMOSPHERE", 1920, 1080, 1.0, {}),
-    ("APP_PLANET", 3840, 2160, 2.0, {}),
-    ("APP_RAYTRACER", 7680, 4320, 1.0, {}),
+    ("APP_EGG", 256, 256, 0.0, {}, 1),                                   # configs[0], the reference's own CPU-runnable case
+    ("APP_EGG", 256, 256, 1.0, {}, 1),
+    ("APP_CLOUDS", 1920, 1080, 1.5, {"cld_march_steps": 128}, 1),        # configs[1], the metric's configuration: EVERY pixel
+    ("APP_ATMOSPHERE", 1920, 1080, 1.0, {}, 4),
+    ("APP_PLANET", 3840, 2160, 2.0, {}, 8),
+    ("APP_RAYTRACER", 7680, 4320, 1.0, {}, 8),
 ]
 
 
-@pytest.mark.parametrize("app,w,h,t,ov", FULL, ids=[c[0] for c in FULL])
-def test_full_size_sampled_rows_match_oracle(app, w, h, t, ov, renderers):
-    """At the bench size the oracle renders a sample of rows (every h/8-th) and they must be bit-equal;
-    the whole frame must be finite, alpha 1, and the 8-way stripe shards must tile it exactly."""
+def _checker():
+    """The reference's own headers (oracle/_ref) when they travelled to this box, else the plain-C restatement."""
+    return (loader.ref_render, "oracle/_ref") if loader.have_ref() else (loader.oracle_render, "oracle/sbx_oracle.c")
+
+
+@pytest.mark.parametrize("app,w,h,t,ov,step", FULL, ids=["%s_%dx%d_t%g" % c[:4] for c in FULL])
+def test_full_size_frames_match_the_reference(app, w, h, t, ov, step, renderers):
+    """At the bench sizes: the metric's frame (and the EGG correctness config) pixel for pixel, the other configs on
+    every `step`-th row (>= 1/8 of the frame), against the reference's own headers; the whole frame must be finite
+    with alpha 1, and the 8-way partitions (row stripes, tile checkerboard) must reproduce it bit for bit."""
+    render, _ = _checker()
     r = renderers(app, None)
     full = r.render(w, h, u_time=t, **ov)
     assert np.isfinite(full).all() and (full[..., 3] == 1.0).all()
-    parts = h // 8
-    sh = abi.Shard(1, parts, parts // 3)          # rows parts//3, parts//3 + parts, ... : 8 rows
-    rows = abi.shard_rows(1, parts, parts // 3, h)
-    want = loader.oracle_render(app, abi.default_params(w, h, t, **ov), shard=sh)
+    sh = abi.Shard(1, step, step // 2)            # rows step//2, step//2 + step, ...
+    rows = abi.shard_rows(1, step, step // 2, h)
+    assert len(rows) * 8 >= h
+    want = render(app, abi.default_params(w, h, t, **ov), shard=sh)
     check(full[rows], want)
-    # the 8-GPU partition of the frame (stripes of 4 rows) reproduces it bit for bit
+    # the 8-GPU partitions of the frame reproduce it bit for bit
     for part in (0, 5):
         got = r.render(w, h, u_time=t, shard=(4, 8, part), **ov)
         assert bits_equal(got, full[abi.shard_rows(4, 8, part, h)])
+
+
+def test_plugin_full_size_clouds_rows_match_the_reference(renderers):
+    """The UNCHANGED app_clouds.h at the metric's size, every 8th row."""
+    app, w, h, t, ov = "APP_CLOUDS", 1920, 1080, 1.5, {"cld_march_steps": 128}
+    render, _ = _checker()
+    got = renderers(app, "plugin").render(w, h, u_time=t, shard=(1, 8, 3), **ov)
+    check(got, render(app, abi.default_params(w, h, t, **ov), shard=abi.Shard(1, 8, 3)))
 
 
 def test_errors_are_loud(renderers):

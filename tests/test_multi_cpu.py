@@ -80,19 +80,26 @@ class _OracleHostRenderer:
     def host_frame_unregister(self, host_ptr):
         assert host_ptr == self.ptr
 
-    def render_frame(self, params, alias, shard, stream=0):
+    def render_frame_part(self, params, alias, shard=None, tile_parts=1, tile_part=0, done_flag=0, done_value=0, stream=0):
         import ctypes
 
-        from shaderbox_b200.abi import shard_rows
+        from shaderbox_b200.abi import shard_rows, tile_part_mask
 
-        rows = shard_rows(shard[0], shard[1], shard[2], params.height)
-        part = loader.oracle_render(self.app, params, shard=Shard(*shard), nthreads=1)
         frame = np.ctypeslib.as_array(ctypes.cast(alias, ctypes.POINTER(ctypes.c_float)), shape=(params.height, params.width, 4))
-        if rows:
-            frame[rows] = part
+        if tile_parts > 1:      # a checkerboard of warp tiles: this part's pixels of every row
+            full = loader.oracle_render(self.app, params, nthreads=1)
+            mask = tile_part_mask(params.width, params.height, tile_parts, tile_part)
+            frame[mask] = full[mask]
+        else:
+            rows = shard_rows(shard[0], shard[1], shard[2], params.height)
+            part = loader.oracle_render(self.app, params, shard=Shard(*shard), nthreads=1)
+            if rows:
+                frame[rows] = part
+        if done_flag:           # what the launch's last thread block does after its pixel stores
+            ctypes.c_uint.from_address(done_flag).value = done_value
 
 
-def _host_frame_worker(rank, world, port, stripe, result_path):
+def _host_frame_worker(rank, world, port, stripe, split, result_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -102,7 +109,7 @@ def _host_frame_worker(rank, world, port, stripe, result_path):
             if rank == 0:
                 shost.array[:] = np.nan
             dist.barrier()
-            shost.render(default_params(W, H, t), stripe)
+            shost.render(default_params(W, H, t), stripe, split=split)
             if rank == 0:
                 np.save(result_path % frame_no, np.array(shost.array))
             dist.barrier()
@@ -111,11 +118,12 @@ def _host_frame_worker(rank, world, port, stripe, result_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,stripe", [(2, 4), (3, 1)])
-def test_shared_host_frame_protocol(tmp_path, world, stripe):
-    """One POSIX-shm frame mapped by every rank, each rank writing its own stripes, completion by the host barrier on
-    the control page: on return from render() rank 0 reads the whole frame."""
+@pytest.mark.parametrize("world,stripe,split", [(2, 4, "rows"), (3, 1, "rows"), (2, 4, "tiles"), (3, 4, "tiles")])
+def test_shared_host_frame_protocol(tmp_path, world, stripe, split):
+    """One anonymous shared-memory frame mapped by every rank, each rank writing its own part (row stripes or a
+    checkerboard of tiles), completion by the per-rank flags on the control page: on return from render() rank 0 reads
+    the whole frame."""
     result = str(tmp_path / "host%d.npy")
-    mp.spawn(_host_frame_worker, args=(world, _free_port(), stripe, result), nprocs=world, join=True)
+    mp.spawn(_host_frame_worker, args=(world, _free_port(), stripe, split, result), nprocs=world, join=True)
     for frame_no, t in enumerate((T, T + 1.0)):
         assert bits_equal(np.load(result % frame_no), loader.oracle_render(APP, default_params(W, H, t)))
