@@ -9,15 +9,23 @@ uniforms (u_res, u_time, aux block).  There is no input data besides those unifo
 output (RGBA32F, 16 B/pixel).
 
   value      frames stay in HBM: CUDA events around each step's launches on the launching stream
-  e2e        the reference-facing call (sbx_render_host through the C ABI): uniforms from the host,
-             frame copied back to pinned host memory, wall time around the synchronous calls
+  e2e        the reference-facing call (sbx_render_host through the C ABI): uniforms from the host, the frame
+             in host memory from sbx_host_alloc (pinned + mapped: the kernel stores into it over PCIe), wall
+             time around the synchronous calls; e2e.pageable_value = the same call with a malloc'd frame
   roofline   mandated HBM figure (16 B/pixel written / kernel time / measured copy peak) -- and the
              FP32-issue figure that actually bounds this path (DESIGN.md "Roofline")
   cpu_baseline  oracle/_ref (the reference's own headers compiled for the host, AVX2+FMA fast-math
              build, all cores) on a bounded sample of rows of the same frame
 
-N > 1: the frame is cut into 4-row stripes dealt round-robin to the ranks (strong scaling); every
-step ends with the frame assembled on rank 0 (see shaderbox_b200/multi.py), inside the timed region.
+  extra_workloads   BASELINE.json configs 3-5 (ATMOSPHERE 1080p, PLANET 4K, RAYTRACER 8K), same measurement
+  frame      digest of the assembled frame (the same sample and 64-bit hash at every N; at N > 1 the
+             frame is also compared bit for bit with rank 0's GPU rendering it alone, inside the run)
+
+N > 1 (one process per GPU, torchrun): the frame is cut into 4-row stripes dealt round-robin to the
+ranks (strong scaling; --split tiles = a checkerboard of warp tiles instead); every rank's render kernel stores its pixels straight into rank 0's frame
+over NVLink and publishes a completion flag behind them; rank 0's stream waits on the flags -- all
+inside the timed region (see shaderbox_b200/multi.py).  single_process_group = the same frame through
+sbx_multi_* (one process driving all GPUs: what a C++ host calls).
 """
 import argparse
 import json
@@ -181,10 +189,12 @@ def run_reference_arm(args):
     value = first["rows"] * w * args.steps / dt * 1e-6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * (h / first["rows"]),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "ms_per_full_frame_extrapolated": dt / args.steps * 1e3 * (h / first["rows"]),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s %dx%d u_time=%g %s" % (app, w, h, t, json.dumps(ov)), "host": "CPU, %d threads" % cores,
-                   "ms_per_step_note": "extrapolated to the full frame from the row sample"},
+                   "step": "one step = the bounded row sample named in cpu_baseline.sample (%d of %d rows); ms_per_step is measured, "
+                           "ms_per_full_frame_extrapolated scales it to the frame" % (first["rows"], h)},
         "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": cores, "kind": first["kind"], "sample": first["sample"]},
         "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -196,217 +206,456 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
+EXTRA_WORKLOADS = ("atmosphere1080", "planet2160", "raytracer4320")   # BASELINE.json configs[2..4]
+
+
+def frame_digest(frame_t):
+    """(sample checksum, 64-bit position-weighted hash of the frame's bit patterns), computed on the GPU.  The sample
+    is the one every line of every N prints (rows ::97, columns ::89, RGB), so lines can be compared across runs."""
+    import torch
+
+    sample = float(frame_t[::97, ::89, :3].double().sum())
+    bits = frame_t.reshape(-1).view(torch.int32).to(torch.int64)
+    acc = 0
+    chunk = 1 << 26
+    for o in range(0, bits.numel(), chunk):
+        b = bits[o:o + chunk]
+        wgt = (torch.arange(o, o + b.numel(), device=b.device, dtype=torch.int64) % 65521) + 1
+        acc = (acc + int((b * wgt).sum())) & 0xFFFFFFFFFFFFFFFF
+    return sample, "%016x" % acc
+
+
+class Job:
+    """One workload on this rank: the renderer, the frame it renders into, and the timed loops."""
+
+    def __init__(self, workload, env, variant=None, stripe=4, split="rows", signal="flags"):
+        import torch
+
+        import shaderbox_b200 as sbx
+        from shaderbox_b200 import multi
+        from shaderbox_b200.abi import default_params
+
+        self.env, self.workload, self.split, self.signal, self.stripe = env, workload, split, signal, stripe
+        self.app, self.w, self.h, self.t, self.ov = WORKLOADS[workload]
+        self.p = default_params(self.w, self.h, self.t, **self.ov)
+        self.r = sbx.Renderer(self.app, device=env.local_rank, variant=variant)
+        self.shared = multi.SharedFrame(self.r, self.w, self.h)          # world 1: a plain frame on this GPU
+        self.stream = torch.cuda.current_stream(env.dev)
+        self.px = self.w * self.h
+
+    def launch(self):
+        self.shared.launch(self.p, self.split, self.stripe, self.signal, stream=self.stream.cuda_stream)
+
+    def step(self):
+        self.launch()
+        self.shared.complete(self.signal, stream=self.stream.cuda_stream)
+
+    def time_device(self, steps, warmup):
+        """`steps` frames, each: [L2 flush, barrier] untimed, then event | this rank's part | event | completion | event.
+        Returns (total step ms: max over ranks, [per-rank mean kernel ms])."""
+        import torch
+        import torch.distributed as dist
+
+        env = self.env
+        for _ in range(max(3, warmup)):
+            self.step()
+            env.flush.zero_()
+        env.barrier()
+        ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(steps)]
+        env.barrier()
+        for k in range(steps):
+            env.flush.zero_()                          # evict the previous frame (and the memo table) from L2, untimed
+            if env.world > 1:
+                dist.barrier()                         # all ranks start the step together
+            ev[k][0].record(self.stream)
+            self.launch()
+            ev[k][1].record(self.stream)
+            self.shared.complete(self.signal, stream=self.stream.cuda_stream)
+            ev[k][2].record(self.stream)
+        env.barrier()
+        kernel = sum(a.elapsed_time(b) for a, b, _ in ev)
+        total = sum(a.elapsed_time(c) for a, _, c in ev)
+        tot = torch.tensor([total], dtype=torch.float64, device=env.dev)
+        per_rank = torch.zeros(env.world, dtype=torch.float64, device=env.dev)
+        per_rank[env.rank] = kernel / steps
+        if env.world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+            dist.all_reduce(per_rank)
+        return float(tot[0]), [float(x) for x in per_rank]
+
+    def digest(self, check_against_single_gpu):
+        """Digest of the assembled frame (rank 0); at N > 1 also compares it, bit for bit, with a render of the whole
+        frame by rank 0's GPU alone."""
+        import torch
+
+        env = self.env
+        self.step()
+        torch.cuda.synchronize(env.dev)
+        env.barrier()
+        out = None
+        if env.rank == 0:
+            frame = self.shared.tensor()
+            sample, h64 = frame_digest(frame)
+            out = {"checksum": sample, "frame_hash": h64}
+            if check_against_single_gpu:
+                alone = torch.empty_like(frame)
+                self.r.render_frame_part(self.p, alone.data_ptr(), stream=self.stream.cuda_stream)
+                torch.cuda.synchronize(env.dev)
+                same = bool(torch.equal(alone.view(torch.int32), frame.view(torch.int32)))
+                out["equals_single_gpu_render"] = same
+                if not same:
+                    raise SystemExit("bench.py: the %d-GPU frame of %s differs from the 1-GPU frame" % (env.world, self.workload))
+        env.barrier()
+        return out
+
+    def time_e2e(self, steps, pageable=False):
+        """The reference-facing call with HOST frames, wall clock around synchronous calls, copies inside.
+        N = 1: sbx_render_host into a frame from sbx_host_alloc (or a pageable numpy frame).
+        N > 1: every rank's kernel stores its part into one host frame shared by the processes."""
+        import ctypes as C
+
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        from shaderbox_b200 import multi
+
+        env = self.env
+        if env.world == 1:
+            nbytes = self.px * 16
+            if pageable:
+                arr = np.empty((self.h, self.w, 4), np.float32)
+                ptr, free = arr.ctypes.data, None
+            else:
+                ptr = self.r.host_alloc(nbytes)
+                free = ptr
+                arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(self.h, self.w, 4))
+
+            def call():
+                self.r.render_host_ptr(self.p, ptr)
+            closer = (lambda: self.r.host_free(free)) if free else (lambda: None)
+        else:
+            shost = multi.SharedHostFrame(self.r, self.w, self.h)
+            arr = shost.array
+
+            def call():
+                shost.render(self.p, self.stripe, split=self.split)
+            closer = shost.close
+        for _ in range(2):
+            call()
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call()
+        env.barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=env.dev)
+        if env.world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        checksum = float(np.asarray(arr[::97, ::89, :3], dtype=np.float64).sum()) if env.rank == 0 else 0.0   # the host frame is read
+        zero_copy = bool(self.r.timing()["zero_copy"]) if env.world == 1 else True
+        closer()
+        return float(dt[0]), checksum, zero_copy
+
+    def close(self):
+        self.shared.close()
+        self.r.close()
+
+
+class Env:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- shaderbox_b200 has no CPU path (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.host_group = None
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.host_group = dist.new_group(backend="gloo")          # host-side waits that keep the GPUs idle
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+
+def cubin_sha256(app, variant):
+    import hashlib
+
+    path = os.path.join(ROOT, "shaderbox_b200", "images", "%s.%s.cubin" % (app, variant))
+    return hashlib.sha256(open(path, "rb").read()).hexdigest() if os.path.exists(path) else None
+
+
+def extra_workload(env, name, steps, args):
+    """One BASELINE.json config besides the metric's, same measurement, compact result."""
+    job = Job(name, env, stripe=args.stripe_rows, split=args.split, signal=args.signal)
+    total_ms, per_rank = job.time_device(steps, 3)
+    dig = job.digest(env.world > 1)
+    e2e_s, e2e_sum, _ = job.time_e2e(steps)
+    tm = job.r.timing()
+    out = None
+    if env.rank == 0:
+        hbm_peak, _, _ = peaks()
+        kernel_ms = max(per_rank)
+        bytes_rank0 = 16.0 * job.px / env.world
+        out = {"workload": "%s %dx%d u_time=%g" % (job.app, job.w, job.h, job.t), "value": job.px * steps / (total_ms * 1e-3) * 1e-6,
+               "unit": "Mpixels/s", "ms_per_step": total_ms / steps, "kernel_ms_per_rank": per_rank, "steps": steps,
+               "e2e": job.px * steps / e2e_s * 1e-6, "e2e_checksum": e2e_sum,
+               "hbm_frac": bytes_rank0 / (kernel_ms * 1e-3) * 1e-9 / hbm_peak, "regs": tm["regs_per_thread"], "ctas_per_sm": tm["blocks_per_sm"]}
+        out.update(dig)
+    job.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    import shaderbox_b200 as sbx
-    from shaderbox_b200 import multi
-    from shaderbox_b200.abi import default_params
+    env = Env()
+    world, rank = env.world, env.rank
+    if world == 1 and (args.format == "rgba8" or args.frames > 1):
+        return run_ours_formats(args, env)
+    if args.format == "rgba8" or args.frames > 1:
+        raise SystemExit("bench.py: --format rgba8 / --frames are 1-GPU measurements")
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- shaderbox_b200 has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
-
-    app, w, h, t, ov = WORKLOADS[args.workload]
-    p = default_params(w, h, t, **ov)
-    r = sbx.Renderer(app, device=local_rank, variant=args.variant)
-    stripe = args.stripe_rows
-    shard = multi.shard_of(rank, world, stripe)
-    rows = multi.part_rows(h, shard)
-    stream = torch.cuda.current_stream(dev)
-    rgba8 = args.format == "rgba8"
-    if rgba8 and world > 1:
-        raise SystemExit("bench.py: --format rgba8 is a 1-GPU measurement")
-    nf = max(1, args.frames)                                  # frames per step (time sequence in one launch)
-    if nf > 1 and (world > 1 or rgba8):
-        raise SystemExit("bench.py: --frames is a 1-GPU float-frame measurement")
-    seq_times = [t + k / 60.0 for k in range(nf)]             # a 60 Hz animation starting at the workload's u_time
-    part = torch.empty((nf * rows, w, 4), dtype=torch.uint8 if rgba8 else torch.float32, device=dev)
-    px_bytes = 4 if rgba8 else 16
-    frame = torch.empty((h, w, 4), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
-    fused = world > 1 and args.gather == "p2p"
-    shared = multi.SharedFrame(r, w, h) if fused else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    launches_per_step = 1 if (world == 1 or fused) else 1 + (world if rank == 0 else 0)
-
-    def step():
-        """kernel (+ gather + unshard at N > 1), all on `stream`"""
-        if nf > 1:
-            r.render_sequence_into(p, seq_times, part.data_ptr(), shard=shard, stream=stream.cuda_stream)
-        elif world == 1:
-            (r.render_rgba8_into if rgba8 else r.render_into)(p, part.data_ptr(), shard=shard, stream=stream.cuda_stream)
-        elif fused:
-            shared.render(p, stripe)
-        else:
-            multi.render_distributed(r, p, stripe, frame_out=frame, part_out=part)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    sampler = ClockSampler(local_rank)   # runs through warm-up + the timed region (nvidia-smi needs ~0.3 s to start)
+    job = Job(args.workload, env, variant=args.variant, stripe=args.stripe_rows, split=args.split, signal=args.signal)
+    sampler = ClockSampler(env.local_rank)   # runs through warm-up + the timed region (nvidia-smi needs ~0.3 s to start)
     if rank == 0:
         sampler.start()
-    for _ in range(max(3, args.warmup)):
-        step()
-        flush.zero_()
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    barrier()
     sampler.mark(0)
     wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()                          # evict the previous frame from L2 (untimed)
-        if world > 1:
-            dist.barrier()                     # all ranks start the step together
-        ev[k][0].record(stream)
-        if world == 1:
-            step()
-            ev[k][1].record(stream)
-        elif fused:
-            r.render_frame(p, shared.ptr, shard=shard, stream=stream.cuda_stream)
-            ev[k][1].record(stream)
-            dist.all_reduce(shared._done)      # stream-ordered "every rank's stripes have landed in rank 0's frame"
-        else:
-            r.render_into(p, part.data_ptr(), shard=shard, stream=stream.cuda_stream)
-            ev[k][1].record(stream)
-            parts = multi.gather_parts(part, w, h, stripe, 0)
-            if parts is not None:
-                for q, prt in enumerate(parts):
-                    if prt.shape[0]:
-                        r.unshard(w, h, multi.shard_of(q, world, stripe), prt.data_ptr(), frame.data_ptr(), stream=stream.cuda_stream)
-        ev[k][2].record(stream)
-    barrier()
+    total_ms, per_rank_kernel = job.time_device(args.steps, args.warmup)
     wall = time.perf_counter() - wall0
     sampler.mark(1)
-    kernel_ms = [a.elapsed_time(b) for a, b, _ in ev]
-    step_ms = [a.elapsed_time(c) for a, _, c in ev]
     clocks = sampler.stop() if rank == 0 else None
-    tm = r.timing()
+    tm = job.r.timing()
+    dig = job.digest(world > 1)
 
-    # max over ranks of the timed total
-    tot = torch.tensor([sum(step_ms), sum(kernel_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    total_ms, total_kernel_ms = float(tot[0]), float(tot[1])
-
-    # ---- e2e: the reference-facing host call, host buffers, copies inside the timed region --------
     if args.no_zero_copy:
-        r.set_option("host_zero_copy", 0)
-    if world == 1:
-        host = torch.empty((nf * rows, w, 4), dtype=torch.uint8 if rgba8 else torch.float32).pin_memory()
-        import ctypes as _C
-        import numpy as _np
-        _times = _np.asarray(seq_times, dtype=_np.float32)
+        job.r.set_option("host_zero_copy", 0)
+    e2e_s, e2e_sum, zero_copy = job.time_e2e(args.steps)
+    e2e_page = job.time_e2e(args.steps, pageable=True) if world == 1 else None
 
-        def e2e_step():
-            if nf > 1:                                                # sbx_render_sequence_host: synchronous
-                r._check(r._L.sbx_render_sequence_host(r._ctx, _C.byref(p), _C.byref(sbx.Shard(*shard)), _times.ctypes.data_as(_C.c_void_p),
-                                                       nf, _C.c_void_p(host.data_ptr())), "sbx_render_sequence_host")
-            else:
-                (r.render_rgba8_host_ptr if rgba8 else r.render_host_ptr)(p, host.data_ptr(), shard=shard)   # sbx_render_host[_rgba8]
-        d2h_bytes = int(px_bytes * rows * w * nf)
-    else:
-        # N ranks: every rank's kernel stores its stripes into ONE host frame shared by the processes (POSIX shared memory,
-        # pinned + mapped per GPU), each over its own PCIe link; complete after each rank's stream sync + a host barrier
-        shost = multi.SharedHostFrame(r, w, h)
-        host = torch.from_numpy(shost.array) if rank == 0 else None
+    extras = {}
+    if not args.no_extra and args.workload == "clouds1080":
+        for name in EXTRA_WORKLOADS:
+            extras[name] = extra_workload(env, name, args.extra_steps, args)
 
-        def e2e_step():
-            shost.render(p, stripe)
-        d2h_bytes = int(16 * rows * w)
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e_local = time.perf_counter() - e0
-    e_t = torch.tensor([e_local], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(e_t[0])
-    checksum = float(host[::97, ::89, :3].double().sum()) if host is not None else 0.0   # the host result is actually read
-    zero_copy = bool(r.timing()["zero_copy"]) if world == 1 else True   # N > 1: SharedHostFrame is mapped host memory by construction
+    group_line = None
+    if world > 1 and not args.no_group:
+        group_line = single_process_group(env, job, args)
 
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_src = peaks()
-        px = w * h * nf
+        px, w, h = job.px, job.w, job.h
         value = px * args.steps / (total_ms * 1e-3) * 1e-6
-        avg_kernel_ms = total_kernel_ms / args.steps
-        alg_bytes = float(px_bytes) * rows * w * nf       # this rank's launch: 16 (RGBA32F) or 4 (RGBA8) B/pixel written, 0 read
+        avg_kernel_ms = max(per_rank_kernel)              # the dominant kernel's launch on the slowest rank
+        alg_bytes = 16.0 * px / world                     # one rank's launch: 16 B/pixel (RGBA32F) written, 0 read
         achieved = alg_bytes / (avg_kernel_ms * 1e-3) * 1e-9
-        traffic = None
+        traffic_db = {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.workload if world == 1 else "", None)
+            traffic_db = json.load(open(tpath))
+        traffic = traffic_db.get(args.workload) if world == 1 else None
+        split_text = {"tiles": "a checkerboard of 8x4 warp tiles dealt to the %d ranks (every rank renders 1/%d of every row)" % (world, world),
+                      "rows": "%d-row stripes round-robin over %d ranks" % (args.stripe_rows, world)}[args.split]
+        signal_text = {"flags": "each launch's last thread block stores a completion flag behind its pixels in rank 0's memory; rank 0's stream waits "
+                                "on the %d flags (cuStreamWaitValue32)" % world,
+                       "nccl": "a 1-element NCCL all-reduce on the launching stream as the completion barrier"}[args.signal]
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s %dx%d u_time=%g %s" % (app, w, h, t, json.dumps(ov)), "variant": tm_variant(r, args), "format": "RGBA8_UNORM" if rgba8 else "RGBA32F", "frames_per_step": nf,
+            "config": {"workload": "%s %dx%d u_time=%g %s" % (job.app, w, h, job.t, json.dumps(job.ov)), "variant": tm_variant(job.r, args),
+                       "format": "RGBA32F", "frames_per_step": 1,
                        "l2": "flushed between steps (256 MiB memset on the same stream, outside the timed events); the frame is write-only",
                        "sharding": "none" if world == 1 else (
-                           "%d-row stripes round-robin over %d ranks; every rank's render kernel stores its rows into rank 0's frame over NVLink "
-                           "(CUDA-IPC peer mapping), then a 1-element all-reduce as the completion barrier, all inside the step" % (stripe, world)
-                           if fused else
-                           "%d-row stripes round-robin over %d ranks, NCCL gather to rank 0 + unshard kernels inside the step" % (stripe, world)),
-                       "grid": tm["grid_blocks"], "block": tm["block_threads"], "regs": tm["regs_per_thread"], "ctas_per_sm": tm["blocks_per_sm"]},
+                           "%s; every rank's render kernel stores its pixels into rank 0's frame over NVLink (CUDA-IPC peer mapping); %s; "
+                           "all inside the step" % (split_text, signal_text)),
+                       "grid": tm["grid_blocks"], "block": tm["block_threads"], "regs": tm["regs_per_thread"], "ctas_per_sm": tm["blocks_per_sm"],
+                       "tail_rows": tm["tail_rows"], "tail_lanes_per_pixel": tm["tail_lanes_per_pixel"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "sbx_render", "kernel_ms": avg_kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "write-only path: 16 B/pixel out, 0 in; the binding roof is instruction issue (see issue_roofline)"},
+            "kernel_ms_per_rank": per_rank_kernel,
             "e2e": {"value": px * args.steps / e2e_s * 1e-6, "unit": "Mpixels/s", "h2d_bytes_per_step": sbx_params_bytes(),
-                    "d2h_bytes_per_step": d2h_bytes if world == 1 else int(16 * w * h), "d2h_bytes_per_step_this_rank": d2h_bytes, "checksum": checksum,
-                    "api": ("sbx_render_host (C ABI) via shaderbox_b200.Renderer.render_host_ptr, pinned host frame" if world == 1 else
-                            "sbx_render_frame on every rank into one shared host frame (sbx_host_frame_register); stream sync, then a host barrier on a shared control page"),
+                    "d2h_bytes_per_step": int(16 * px), "d2h_bytes_per_step_this_rank": int(16 * px / world), "checksum": e2e_sum,
+                    "api": ("sbx_render_host (C ABI) into a frame from sbx_host_alloc (pinned + mapped: what INTEGRATION.md tells a host to use)" if world == 1 else
+                            "sbx_render_frame_part on every rank into one shared host frame (sbx_host_frame_register); each launch publishes a completion "
+                            "flag in the frame's control page, every rank's host polls the %d flags" % world),
                     "d2h": "kernel stores straight into the pinned+mapped host frame (zero-copy over PCIe)" if zero_copy
-                           else "frame assembled in HBM, then one async copy to pinned host memory"},
-            "gpu_launches": launches_per_step * args.steps,
+                           else "frame assembled in HBM, then one async copy to host memory",
+                    "loop": "back-to-back synchronous calls, wall clock; NO L2 flush and no per-step barrier (unlike `value`), so the two are not like for like"},
+            "frame": dig,
+            "gpu_launches": args.steps,
             "clocks": clocks,
             "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
             "kernel_only": {"ms": avg_kernel_ms, "mpix_s": px / (avg_kernel_ms * 1e-3) * 1e-6 if world == 1 else None},
         }
+        if e2e_page is not None:
+            line["e2e"]["pageable_value"] = px * args.steps / e2e_page[0] * 1e-6
+            line["e2e"]["pageable_note"] = "same call with a malloc'd (pageable) frame: rendered in HBM, then cuMemcpyDtoHAsync"
+        if extras:
+            line["extra_workloads"] = extras
+        if group_line:
+            line["single_process_group"] = group_line
         if world == 1 and not args.no_cpu:
             cb = cpu_reference_rate(args.workload, budget_s=args.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-            line["fp32_issue"] = fp32_issue(args.workload, avg_kernel_ms, sm_max_mhz, clocks)
-        if world == 1 and nf == 1 and not rgba8 and os.path.exists(tpath):
+            line["reference_work"] = reference_work(args.workload, avg_kernel_ms, sm_max_mhz, clocks)
+        winst = traffic_db.get(args.workload + "_warp_inst")
+        if world == 1 and winst and args.variant in (None, "native"):
             # the roof that binds: issue slots.  Warp instructions per launch are a property of (kernel image, workload),
-            # counted once by ncu (profiles/, smsp__inst_executed.sum); the time is this run's.
-            winst = json.load(open(tpath)).get(args.workload + "_warp_inst")
-            if winst and args.variant in (None, "native"):
-                clk = (clocks or {}).get("sm_mhz") or sm_max_mhz
-                slots = 148 * 4 * clk * 1e6 * avg_kernel_ms * 1e-3
-                line["issue_roofline"] = {"bound": "issue", "warp_inst_per_launch": winst, "achieved": winst / (avg_kernel_ms * 1e-3) * 1e-9,
-                                          "peak": 148 * 4 * clk * 1e-3, "unit": "G warp-inst/s", "frac": winst / slots,
-                                          "source": "ncu smsp__inst_executed.sum (profiles/traffic.json) / live kernel time; peak = 148 SMs x 4 schedulers x SM clock"}
+            # counted once by ncu (profiles/, smsp__inst_executed.sum); the time is this run's.  The count is only valid
+            # for the image it was taken on: its SHA-256 is stored beside it.
+            image = "hybrid" if tm["tail_rows"] > 0 else "native"
+            sha_now, sha_then = cubin_sha256(job.app, image), traffic_db.get(args.workload + "_cubin_sha256")
+            clk = (clocks or {}).get("sm_mhz") or sm_max_mhz
+            slots = 148 * 4 * clk * 1e6 * avg_kernel_ms * 1e-3
+            line["issue_roofline"] = {"bound": "issue", "warp_inst_per_launch": winst, "achieved": winst / (avg_kernel_ms * 1e-3) * 1e-9,
+                                      "peak": 148 * 4 * clk * 1e-3, "unit": "G warp-inst/s", "frac": winst / slots,
+                                      "stale": sha_now != sha_then, "image": image, "image_sha256": sha_now,
+                                      "source": "ncu smsp__inst_executed.sum (profiles/traffic.json) / live kernel time; peak = 148 SMs x 4 schedulers x SM clock"}
         print(json.dumps(line), file=args.json_out, flush=True)
-    if world > 1:
-        shost.close()
-    if shared is not None:
-        shared.close()
-    r.close()
+    job.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+def single_process_group(env, job, args):
+    """The same frame through sbx_multi_* (include/sbx.h): ONE process (rank 0's) drives every GPU of the run -- the call
+    a C++ host makes.  The other ranks wait on the host (gloo), their GPUs idle but for rank 0's work."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import shaderbox_b200 as sbx
+
+    out = None
+    torch.cuda.synchronize(env.dev)
+    dist.barrier(group=env.host_group)
+    if env.rank == 0:
+        try:
+            m = sbx.MultiRenderer(job.app, n_gpus=env.world, variant=args.variant)
+            p, px = job.p, job.px
+            for _ in range(3):
+                m.render_device(p)
+            m.sync()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                m.render_device(p)
+            m.sync()
+            dev_s = time.perf_counter() - t0
+            kms = m.kernel_ms()
+            host = m.host_alloc(px * 16)
+            arr = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_float)), shape=(job.h, job.w, 4))
+            for _ in range(2):
+                m.render_host_ptr(p, host)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                m.render_host_ptr(p, host)
+            host_s = time.perf_counter() - t0
+            out = {"api": "sbx_multi_render_device / sbx_multi_render_host (one process, %d GPUs)" % env.world,
+                   "value": px * args.steps / dev_s * 1e-6, "e2e": px * args.steps / host_s * 1e-6, "unit": "Mpixels/s",
+                   "timing": "wall clock around back-to-back frames (pipelined on the device path), no L2 flush",
+                   "kernel_ms_per_gpu": kms, "checksum": float(np.asarray(arr[::97, ::89, :3], dtype=np.float64).sum())}
+            m.host_free(host)
+            m.close()
+        except Exception as e:   # noqa: BLE001 -- an extra, must not cost the headline line
+            out = {"error": repr(e)}
+    dist.barrier(group=env.host_group)
+    return out
+
+
+def run_ours_formats(args, env):
+    """1-GPU side measurements: the 8-bit swap-chain format and time sequences in one launch."""
+    import ctypes as _C
+
+    import numpy as _np
+    import torch
+
+    import shaderbox_b200 as sbx
+    from shaderbox_b200.abi import default_params
+
+    app, w, h, t, ov = WORKLOADS[args.workload]
+    p = default_params(w, h, t, **ov)
+    r = sbx.Renderer(app, device=env.local_rank, variant=args.variant)
+    rgba8 = args.format == "rgba8"
+    nf = max(1, args.frames)
+    seq_times = [t + k / 60.0 for k in range(nf)]             # a 60 Hz animation starting at the workload's u_time
+    stream = torch.cuda.current_stream(env.dev)
+    part = torch.empty((nf * h, w, 4), dtype=torch.uint8 if rgba8 else torch.float32, device=env.dev)
+    px_bytes = 4 if rgba8 else 16
+
+    def step():
+        if nf > 1:
+            r.render_sequence_into(p, seq_times, part.data_ptr(), stream=stream.cuda_stream)
+        else:
+            (r.render_rgba8_into if rgba8 else r.render_into)(p, part.data_ptr(), stream=stream.cuda_stream)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+        env.flush.zero_()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        env.flush.zero_()
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    host = torch.empty((nf * h, w, 4), dtype=torch.uint8 if rgba8 else torch.float32).pin_memory()
+    _times = _np.asarray(seq_times, dtype=_np.float32)
+
+    def e2e_step():
+        if nf > 1:
+            r._check(r._L.sbx_render_sequence_host(r._ctx, _C.byref(p), None, _times.ctypes.data_as(_C.c_void_p), nf,
+                                                   _C.c_void_p(host.data_ptr())), "sbx_render_sequence_host")
+        else:
+            (r.render_rgba8_host_ptr if rgba8 else r.render_host_ptr)(p, host.data_ptr())
+    for _ in range(2):
+        e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    px = w * h * nf
+    hbm_peak, _, peak_src = peaks()
+    kernel_ms = total_ms / args.steps
+    line = {"metric": METRIC, "value": px * args.steps / (total_ms * 1e-3) * 1e-6, "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s %dx%d u_time=%g %s" % (app, w, h, t, json.dumps(ov)), "format": "RGBA8_UNORM" if rgba8 else "RGBA32F",
+                       "frames_per_step": nf, "l2": "flushed between steps"},
+            "roofline": {"bound": "hbm", "achieved": px_bytes * px / (kernel_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": px_bytes * px / (kernel_ms * 1e-3) * 1e-9 / hbm_peak, "traffic": None, "peak_source": peak_src},
+            "e2e": {"value": px * args.steps / e2e_s * 1e-6, "unit": "Mpixels/s", "h2d_bytes_per_step": sbx_params_bytes(),
+                    "d2h_bytes_per_step": int(px_bytes * px), "checksum": float(host[::97, ::89, :3].double().sum())},
+            "gpu_launches": args.steps}
+    print(json.dumps(line), file=args.json_out, flush=True)
+    r.close()
+    return 0
+
+
 def tm_variant(r, args):
-    return args.variant or "default (native if present, else plugin)"
+    return args.variant or "default (native / hybrid if present, else plugin)"
 
 
 def sbx_params_bytes():
@@ -417,8 +666,10 @@ def sbx_params_bytes():
     return ctypes.sizeof(Params)
 
 
-def fp32_issue(workload, kernel_ms, sm_max_mhz, clocks):
-    """Algorithmic FP32 lane-instructions (oracle call counters x COST) / kernel time / issue peak."""
+def reference_work(workload, kernel_ms, sm_max_mhz, clocks):
+    """How much of the REFERENCE's arithmetic a frame stands for: oracle call counters x a cost table (SASS instruction
+    counts of sbx_math.h), as a lane-instruction rate.  Not a roofline: hash(n) calls the memo table serves still
+    count as the reference's sin, so the rate exceeds the machine's issue peak -- it measures work avoided."""
     from oracle import loader
     from shaderbox_b200.abi import Shard, default_params
 
@@ -434,10 +685,9 @@ def fp32_issue(workload, kernel_ms, sm_max_mhz, clocks):
     alg = (ops_px + noise_px) * w * h
     clk = (clocks or {}).get("sm_mhz") or sm_max_mhz
     peak = 148 * 128 * clk * 1e6
-    return {"calls_per_pixel": per_px, "alg_lane_instr_per_frame": alg, "achieved_lane_instr_per_s": alg / (kernel_ms * 1e-3),
-            "peak_lane_instr_per_s": peak, "frac": alg / (kernel_ms * 1e-3) / peak, "clock_mhz_used": clk,
-            "note": "call counts from the oracle on %d sampled rows; cost table in bench.py COST (SASS counts of sbx_math.h); "
-                    "hash(n) calls served by the memo table still count as the reference's sin" % rows}
+    return {"calls_per_pixel": per_px, "reference_lane_instr_per_frame": alg, "reference_lane_instr_per_s": alg / (kernel_ms * 1e-3),
+            "machine_lane_instr_per_s": peak, "work_avoided_factor": alg / (kernel_ms * 1e-3) / peak, "clock_mhz_used": clk,
+            "note": "call counts from the oracle on %d sampled rows; cost table in bench.py COST; NOT a fraction of peak" % rows}
 
 
 def _stdout_for_json_only():
@@ -458,8 +708,13 @@ def main():
     ap.add_argument("--workload", default="clouds1080", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default=None, help="native | plugin (default: native if present)")
     ap.add_argument("--stripe-rows", type=int, default=4)
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: p2p = render kernels store into rank 0's frame over NVLink; nccl = compacted parts + ncclGather + unshard")
+    ap.add_argument("--split", default="rows", choices=["tiles", "rows"],
+                    help="N>1: how the frame is cut: a checkerboard of warp tiles (balanced by construction) or interleaved row stripes")
+    ap.add_argument("--completion", dest="signal", default="flags", choices=["flags", "nccl"],
+                    help="N>1: completion = in-kernel flags in rank 0's memory + cuStreamWaitValue32, or a 1-element NCCL all-reduce")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads (BASELINE configs 3-5)")
+    ap.add_argument("--extra-steps", type=int, default=20)
+    ap.add_argument("--no-group", action="store_true", help="N>1: skip the single-process sbx_multi_* measurement")
     ap.add_argument("--format", default="f32", choices=["f32", "rgba8"],
                     help="frame format: raw float4 (BASELINE.json) or the 8-bit swap-chain format of the reference's presenting hosts")
     ap.add_argument("--frames", type=int, default=1, help="frames per step: a u_time sequence rendered by ONE launch (sbx_render_sequence_*)")

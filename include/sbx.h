@@ -96,6 +96,9 @@ typedef struct sbx_ctx sbx_ctx;
 /* Fill *p with the reference defaults (src/uniform_buffer.h:41-58), width x height, u_time = 0. */
 int sbx_default_params(sbx_params* p, int width, int height);
 
+/* Number of CUDA devices the driver shows (0 without a driver / device); never fails. */
+int sbx_device_count(void);
+
 /* Create a context on CUDA device `device` (primary context; interoperates with torch). */
 int sbx_create(int device, sbx_ctx** out);
 void sbx_destroy(sbx_ctx* ctx);
@@ -211,8 +214,8 @@ int sbx_frame_read(sbx_ctx* ctx, const float* dev, float* host, size_t bytes, vo
  * The reference's hosts are single programs with one render loop (hlsltoy's message loop,
  * util/hlsltoy/src/hlsltoy.cpp:494-520; VML's SDL_app.cpp): a group gives such a program every GPU of the box
  * behind one call per frame.  devices = NULL means GPUs 0 .. n_gpus-1; a device may be listed more than once (the
- * parts then share that GPU -- useful to exercise the N-part path on a 1-GPU machine).  Each GPU renders a
- * checkerboard of 8x4 warp tiles (sbx_frame_part) straight into the destination:
+ * parts then share that GPU -- useful to exercise the N-part path on a 1-GPU machine).  Each GPU renders its
+ * 4-row stripes of the frame (sbx_frame_part) straight into the destination:
  *   sbx_multi_render_device  the group's frame in the FIRST device's memory (peers store over NVLink); asynchronous:
  *                            the frame is complete for work enqueued afterwards on sbx_multi_stream(), or after
  *                            sbx_multi_sync().  *dev_frame_out stays owned by the group.
@@ -249,9 +252,10 @@ int sbx_bake_noise_volume_device(sbx_ctx* ctx, int size, int z0, int nz, float* 
 int sbx_bake_noise_volume_host(sbx_ctx* ctx, int size, int z0, int nz, float* host_rgba);
 int sbx_dds_volume_header(int size, unsigned char* out, int capacity);
 
-/* Options: "tail_waves_x100" T (default 100) / "tail_max_waves_x100" M: with the default variant of an app that ships a
- * hybrid image, a launch smaller than M/100 waves of resident warps marches its last T/100 waves' worth of rows with
- * 4 lanes per pixel (the tail of the launch drains 4 times faster) and the rest with one; 0 = never.
+/* Options: "tail_waves_x100" T (default 0 = off) / "tail_max_waves_x100" M: with the default variant of an app that
+ * ships a hybrid image, a launch smaller than M/100 waves of resident warps marches its last T/100 waves' worth of
+ * rows with 4 lanes per pixel and the rest with one (measured on B200: it does not beat the whole-launch choice
+ * below, DESIGN.md 7b -- the long warps are the ones just above the horizon, not the last ones).
  * "use_hash_table" 0|1, "hash_table_log2" 9..22 (noise_iq memo table), "host_zero_copy" 0|1,
  * "coop_waves_x100" W (default 250): with the default variant, launches smaller than W/100 waves of resident warps
  * use the app's 4-lanes-per-pixel cooperative image, launches smaller than 2W/100 waves the 2-lane one, if
@@ -259,6 +263,11 @@ int sbx_dds_volume_header(int size, unsigned char* out, int capacity);
 int sbx_set_option(sbx_ctx* ctx, const char* key, int value);
 
 int sbx_last_timing(sbx_ctx* ctx, sbx_timing* out);
+/* Profiling hook.  Kernel images built with -DSBX_TRACE (csrc/Makefile `make trace`, variants "native_trace" /
+ * "coop_trace" / "hybrid_trace"; not shipped by default) record, per warp of a launch, 4 x 64-bit words
+ * { start ns, end ns, SM id, region } at dev_records[4 * warp] (%globaltimer).  The buffer must hold
+ * 4 * (grid_blocks * block_threads / 32) words; NULL switches recording off.  Ordinary images ignore it. */
+int sbx_set_trace_buffer(sbx_ctx* ctx, unsigned long long* dev_records);
 const char* sbx_last_error(sbx_ctx* ctx_or_null);
 const char* sbx_strerror(int status);
 const char* sbx_version(void);

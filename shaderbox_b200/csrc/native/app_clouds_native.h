@@ -112,7 +112,9 @@ SBX_FN float density_view(float2 pos_xy, float pos_z) {
     const float guard = 1e-5f;
     sbx_mx = pos_xy.x; sbx_my = pos_xy.y;
     float t = sbx_octave(pxy, pz, sbx_mz0, sbx_ys0) * .5f;            // 0 + n*.5 == n*.5 (n >= +0)
-#ifndef SBX_X_NOLAZY
+#if !defined(SBX_X_NOLAZY) && defined(SBX_X_LAZY1)
+    // exit after the first octave: provable, but it fires on 2 % of the samples (ncu source counters, profiles/r02c) and
+    // keeps the second octave's table loads from being issued beside the first's: without it +1 % (1 lane), +2 % (4 lanes)
     if (t <= sbx_cov - .4375f - guard) return 0.0f;
 #endif
     pxy = pk_mul(pxy, 2.64f); pz *= 2.64f;
@@ -265,7 +267,43 @@ template <bool BOUNDED> SBX_FN vec4 render_clouds(_in(ray_t) eye) {   // :153-20
 // P times shorter: frames that are small for the machine (one GPU's share of a 1080p frame at 8
 // GPUs is ~2 waves of warps) no longer end in a long single-warp tail, and the lanes of a warp
 // sit on neighbouring steps of the same rays, which keeps their branches and table lines together.
-template <bool BOUNDED> SBX_FN vec4 render_clouds_coop(_in(ray_t) eye, bool active) {
+// The three pows a cloud pixel needs before its march -- the two sun lobes of render_sky_color (:42-43) and the
+// Henyey-Greenstein denominator (volumetric.h:27-33 via :121) -- are independent: the lanes of a pixel compute one
+// each (same function, same arguments as the one-lane path, so the same bits) and pass them round with shuffles.
+SBX_FN void sbx_coop_pows(_in(vec3) eye_dir, float& lobe1500, float& lobe10, float& hg_pow) {
+    const int P = SBX_COOP_LANES;
+    const int lane = threadIdx.x & 31, phase = lane % P, base = lane - phase;
+    const float sun_amount = max(dot(eye_dir, sun_dir), 0.0f);
+    const float mu = clamp(dot(sun_dir, eye_dir), 0.0f, 1.0f);
+    float mine[(3 + P - 1) / P];
+#pragma unroll
+    for (int k = 0; k * P < 3; ++k) {
+        const int which = k * P + phase;            // 0: sun_amount^1500, 1: sun_amount^10, 2 (and any spare lane): the HG power
+        const float b = which < 2 ? sun_amount : 1.0f + hg_g * hg_g - 2.0f * hg_g * mu;
+        const float e = which == 0 ? 1500.0f : which == 1 ? 10.0f : 1.5f;
+        mine[k] = pow(b, e);
+    }
+    lobe1500 = __shfl_sync(0xffffffffu, mine[0], base);
+    lobe10 = __shfl_sync(0xffffffffu, mine[1 / P], base + 1 % P);
+    hg_pow = __shfl_sync(0xffffffffu, mine[2 / P], base + 2 % P);
+}
+
+// linear_to_srgb (src/util.h:72-77 via src/main.h:52) for a pixel marched by several lanes: one channel per lane
+SBX_FN vec3 sbx_coop_encode(_in(vec3) color) {
+    const int P = SBX_COOP_LANES;
+    const int lane = threadIdx.x & 31, phase = lane % P, base = lane - phase;
+    float mine[(3 + P - 1) / P];
+#pragma unroll
+    for (int k = 0; k * P < 3; ++k) {
+        const int which = k * P + phase;
+        const float c = which == 0 ? color.x : which == 1 ? color.y : color.z;
+        mine[k] = pow(c, 1.0f / 2.2f);
+    }
+    return vec3(__shfl_sync(0xffffffffu, mine[0], base), __shfl_sync(0xffffffffu, mine[1 / P], base + 1 % P),
+                __shfl_sync(0xffffffffu, mine[2 / P], base + 2 % P));
+}
+
+template <bool BOUNDED> SBX_FN vec4 render_clouds_coop(_in(ray_t) eye, bool active, float hg_pow) {
     const int P = SBX_COOP_LANES;
     const int lane = threadIdx.x & 31, phase = lane % P, base = lane - phase;
     const vec3 projection = eye.direction / eye.direction.y;
@@ -276,7 +314,7 @@ template <bool BOUNDED> SBX_FN vec4 render_clouds_coop(_in(ray_t) eye, bool acti
     const float band = (sbx_cov + .0135f) - sbx_cov;
     sbx_band_lo = band > 0.0f ? 0.0f : -__int_as_float(0x7f800000);
     sbx_band_hi = band > 0.0f ? band : __int_as_float(0x7f800000);
-    sbx_phase = henyey_greenstein_phase_func(clamp(dot(sun_dir, eye.direction), 0.0f, 1.0f));
+    sbx_phase = (1.0f - hg_g * hg_g) / ((4.0f + PI) * hg_pow);   // henyey_greenstein_phase_func (volumetric.h:27-33) on the shared pow
 
     const float2 origin_xy = pk(origin.x, origin.y), proj_xy = pk(projection.x, projection.y);
     float transmittance = 1.0f, radiance = 0.0f, alpha = 0.0f;
@@ -285,33 +323,38 @@ template <bool BOUNDED> SBX_FN vec4 render_clouds_coop(_in(ray_t) eye, bool acti
     float t = 0.0f;                                    // the reference's t of step `phase`: 0 (+ dt) (+ dt) ...
     for (int q = 0; q < phase; ++q) t += dt;
     bool done = !active;
-    for (int r = 0; r * P < steps; ++r) {
-        if (__all_sync(0xffffffffu, done)) break;
+    for (int r = __all_sync(0xffffffffu, done) ? steps : 0; r * P < steps; ++r) {   // (a warp of rays below the horizon marches nothing)
         const int i = r * P + phase;
-        float T_i = 2.0f, A = 0.0f;                    // T_i = 2 (impossible for exp(-x), x >= 0): the step integrates nothing
+        float T_i = 1.0f, A = 0.0f;
+        bool hit = false;                              // this lane's step met cloud (integrate_volume's density test, :132)
         if (!done && i < steps) {
             const float2 pos_xy = pk_add(origin_xy, pk_mul(proj_xy, t));
             const float pos_z = origin.z + t * projection.z;
             const float density = density_view(pos_xy, pos_z);
             if (!(density < .005f)) {
+                hit = true;
                 T_i = sbx_beer_lambert<BOUNDED>(density, dt);
                 A = (density * sigma_scattering) * illuminate_volume<BOUNDED>(pos_xy, pos_z, sun_dir);
             }
         }
 #pragma unroll
         for (int q = 0; q < P; ++q) t += dt;           // this lane's next step is P steps on
-        if (__any_sync(0xffffffffu, T_i != 2.0f)) {    // rounds in which no lane of the warp met cloud change nothing
+        const unsigned hits = __ballot_sync(0xffffffffu, hit) >> base;   // bit q: step r*P + q of this pixel integrates
+        if (__any_sync(0xffffffffu, hit)) {            // rounds in which no lane of the warp met cloud change nothing
 #pragma unroll
             for (int q = 0; q < P; ++q) {              // steps r*P .. r*P+P-1 in order
                 const float Tq = __shfl_sync(0xffffffffu, T_i, base + q);
                 const float Aq = __shfl_sync(0xffffffffu, A, base + q);
-                if (!done && Tq != 2.0f) {
-                    transmittance *= Tq;
-                    radiance += Aq * transmittance * dt;
-                    alpha += (1.0f - Tq) * (1.0f - alpha);
-                    if (alpha > .999f) done = true;    // :197 (alpha only changes in a cloud step)
-                }
+                // branch-free: a step that integrates nothing multiplies by 1 and adds +0, which change no bit of
+                // the accumulators whatever they hold (x * 1 == x; x + 0 == x for every x but -0, and none of them can
+                // be -0: they start at 1, +0, +0 and a sum only yields -0 from two -0 operands)
+                const bool use = !done && ((hits >> q) & 1u);
+                transmittance *= use ? Tq : 1.0f;
+                radiance += use ? Aq * transmittance * dt : 0.0f;
+                alpha += use ? (1.0f - Tq) * (1.0f - alpha) : 0.0f;
+                done = done || (use && alpha > .999f); // :197 (alpha only changes in a cloud step)
             }
+            if (__all_sync(0xffffffffu, done)) break;  // `done` only changes in a merge: the exit vote is taken here alone
         }
     }
 #pragma unroll
@@ -372,20 +415,27 @@ static __device__ __noinline__ float4 sbx_generic_pixel(const sbx_launch* L, flo
 }
 
 SBX_FN vec3 render(_in(ray_t) eye_ray, _in(vec3) point_cam) {   // :204-218
-    const vec3 sky = render_sky_color(eye_ray.direction);
     sbx_kmax = 0u;
     const bool bounded = abs(sigma_scattering * (cld_thick / float(cld_march_steps))) < 80.0f;   // see sbx_beer_lambert
+    vec3 sky;
     vec4 cld;
 #if SBX_COOP_LANES > 1
     if (sbx_coop) {   // warp-uniform (a compile-time constant unless the image is a hybrid)
+        float lobe1500, lobe10, hg_pow;
+        sbx_coop_pows(eye_ray.direction, lobe1500, lobe10, hg_pow);
+        sky = mix(vec3(.0f, .1f, .4f), vec3(.3f, .6f, .8f), 1.0f - eye_ray.direction.y);   // render_sky_color (:36-46)
+        sky += sun_color * min(lobe1500 * 5.0f, 1.0f);
+        sky += sun_color * min(lobe10 * .6f, 1.0f);
+        sky = abs(sky);
         const bool below = dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f;
         // (the uniforms, hence `bounded`, are the same in every lane: the whole warp takes one instantiation)
-        cld = bounded ? render_clouds_coop<true>(eye_ray, !below) : render_clouds_coop<false>(eye_ray, !below);
+        cld = bounded ? render_clouds_coop<true>(eye_ray, !below, hg_pow) : render_clouds_coop<false>(eye_ray, !below, hg_pow);
         if (below) return sky;
     } else
 #endif
     {
 #if SBX_LANES_PER_PIXEL == 1
+        sky = render_sky_color(eye_ray.direction);
         if (dot(eye_ray.direction, vec3(0.0f, 1.0f, 0.0f)) < 0.05f) return sky;
         cld = bounded ? render_clouds<true>(eye_ray) : render_clouds<false>(eye_ray);
 #endif
@@ -400,4 +450,8 @@ SBX_FN vec3 render(_in(ray_t) eye_ray, _in(vec3) point_cam) {   // :204-218
 }
 
 #define FOV 1.0f   // :220
+#if SBX_COOP_LANES > 1
+// main.h's sRGB encode (src/main.h:52), one channel per lane when several lanes march the pixel
+#define SBX_APP_ENCODE(color) (sbx_coop ? sbx_coop_encode(color) : linear_to_srgb(color))
+#endif
 #include "main.h"

@@ -130,7 +130,11 @@ int main(int argc, char** argv) {
         sbx_ctx* ctx = nullptr;
         int st;
         if (gpus > 1) {
-            st = sbx_multi_create(nullptr, gpus, &group);
+            // parts beyond the GPUs the box has share them round-robin (the N-part path on a smaller box)
+            const int have = sbx_device_count();
+            std::vector<int> devices;
+            for (int i = 0; i < gpus; ++i) devices.push_back(have > 0 ? (device + i) % have : i);
+            st = sbx_multi_create(devices.data(), gpus, &group);
             if (st != SBX_OK) { fprintf(stderr, "sbx_multi_create(%d): %s: %s\n", gpus, sbx_strerror(st), sbx_last_error(nullptr)); return 1; }
             st = sbx_multi_load_app(group, app, variant);
             if (st != SBX_OK) { fprintf(stderr, "sbx_multi_load_app: %s: %s\n", sbx_strerror(st), sbx_multi_last_error(group)); return 1; }

@@ -150,8 +150,9 @@ struct sbx_ctx {
     int opt_use_hash = 1;
     int opt_zero_copy = 1;        // sbx_render_host: store straight into pinned+mapped host frames
     int opt_coop_waves_x100 = 250;   // use the cooperative image when the grid is below this many waves of resident warps
-    int opt_tail_waves_x100 = 100;   // hybrid image: march the last this-many waves of the launch with several lanes per pixel
+    int opt_tail_waves_x100 = 0;     // hybrid image (opt-in): march the last this-many waves of the launch with 4 lanes per pixel
     int opt_tail_max_waves_x100 = 1200;  // ... for launches below this many waves (a long launch amortises its tail anyway)
+    CUdeviceptr trace = 0;           // profiling hook: per-warp records of the next launches (trace images only)
     CUdeviceptr done_counters = 0;   // ring of CTA counters for launches that signal a completion flag
     unsigned done_seq = 0;
 
@@ -336,6 +337,14 @@ int sbx_default_params(sbx_params* p, int width, int height) {
     p->fog_density = 0.1f;
     p->fog_falloff = 0.5f;
     return SBX_OK;
+}
+
+int sbx_device_count(void) {
+    std::string err;
+    driver_api* cu = load_driver(&err);
+    int n = 0;
+    if (!cu || cu->Init(0) != CUDA_SUCCESS || cu->DeviceGetCount(&n) != CUDA_SUCCESS) return 0;
+    return n;
 }
 
 int sbx_create(int device, sbx_ctx** out) {
@@ -587,6 +596,7 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const launch_job& jo
     L.hash_len = ctx->hash_len;
     L.hash_span = ctx->hash_len;
     L.lut = (const void*)ctx->lut;
+    L.trace = (unsigned long long*)(uintptr_t)ctx->trace;
     if (job.done_flag) {
         if (!ctx->done_counters) {
             SBX_TRY(ctx->cu->MemAlloc(&ctx->done_counters, 64 * sizeof(unsigned)), "cuMemAlloc(done counters)");
@@ -967,6 +977,12 @@ int sbx_dds_volume_header(int size, unsigned char* out, int capacity) {
     w[36] = 0u;                                          // miscFlags2
     std::memcpy(out, w, 148);
     return 148;
+}
+
+int sbx_set_trace_buffer(sbx_ctx* ctx, unsigned long long* dev_records) {
+    if (!ctx) return SBX_ERR_INVALID;
+    ctx->trace = (CUdeviceptr)(uintptr_t)dev_records;
+    return SBX_OK;
 }
 
 int sbx_last_timing(sbx_ctx* ctx, sbx_timing* out) {

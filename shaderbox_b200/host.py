@@ -74,6 +74,7 @@ def lib():
         L.sbx_multi_last_timing.argtypes = [C.c_void_p, P(C.c_float), C.c_int]
         L.sbx_multi_last_error.argtypes = [C.c_void_p]
         L.sbx_multi_last_error.restype = C.c_char_p
+        L.sbx_set_trace_buffer.argtypes = [C.c_void_p, C.c_void_p]
         L.sbx_frame_alloc.argtypes = [C.c_void_p, C.c_size_t, P(C.c_void_p)]
         L.sbx_frame_free.argtypes = [C.c_void_p, C.c_void_p]
         L.sbx_frame_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
@@ -104,7 +105,7 @@ EXPORTS = (
     "sbx_render_frame_part", "sbx_stream_wait_flags", "sbx_host_alloc", "sbx_host_free",
     "sbx_multi_create", "sbx_multi_destroy", "sbx_multi_gpus", "sbx_multi_ctx", "sbx_multi_load_app", "sbx_multi_set_option",
     "sbx_multi_render_device", "sbx_multi_render_host", "sbx_multi_stream", "sbx_multi_sync", "sbx_multi_last_timing",
-    "sbx_multi_last_error",
+    "sbx_multi_last_error", "sbx_device_count", "sbx_set_trace_buffer",
 )
 
 
@@ -241,6 +242,9 @@ class Renderer:
         self._check(self._L.sbx_stream_wait_flags(self._ctx, C.c_void_p(dev_flags_ptr), int(n), int(value), C.c_void_p(stream)),
                     "sbx_stream_wait_flags")
 
+    def set_trace_buffer(self, dev_ptr):
+        self._check(self._L.sbx_set_trace_buffer(self._ctx, C.c_void_p(dev_ptr or None)), "sbx_set_trace_buffer")
+
     def host_alloc(self, nbytes):
         """A pinned + mapped host frame (sbx_host_alloc): sbx_render_host stores into it directly from the kernel."""
         out = C.c_void_p()
@@ -327,7 +331,7 @@ class Renderer:
 
 
 class MultiRenderer:
-    """One frame over several GPUs from THIS process (sbx_multi_*): every GPU renders a checkerboard of warp tiles of
+    """One frame over several GPUs from THIS process (sbx_multi_*): every GPU renders its 4-row stripes of
     the frame straight into the destination.  `devices` may repeat a device (the parts then share it)."""
 
     def __init__(self, app, devices=None, n_gpus=None, variant=None):

@@ -15,5 +15,9 @@ SBX_FN void mainImage(vec4& fragColor, const vec2& fragCoord) {
     const ray_t ray = get_primary_ray(point_cam, eye, look_at);
     const vec3 color = render(ray, point_cam);
 
+#ifdef SBX_APP_ENCODE      // a hand-written scene kernel may spread the three pows over the lanes that share the pixel
+    fragColor = vec4(SBX_APP_ENCODE(color), 1.0f);
+#else
     fragColor = vec4(linear_to_srgb(color), 1.0f);
+#endif
 }

@@ -138,6 +138,11 @@ sbx_render(const __grid_constant__ sbx_launch L) {
 
     int warp = blockIdx.x * SBX_WARPS_PER_CTA + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+#ifdef SBX_TRACE
+    const int trace_warp = warp;
+    unsigned long long trace_t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
+#endif
 #if SBX_HYBRID_LANES > 1
     // hybrid image: the first reg[0].warps warps render 8x4 tiles with one lane per pixel, the warps after them
     // render the remaining (upper) rows with SBX_HYBRID_LANES lanes per pixel -- the tail of the launch is cut
@@ -191,6 +196,17 @@ sbx_render(const __grid_constant__ sbx_launch L) {
             else __stcs(reinterpret_cast<float4*>(L.out) + at, make_float4(c.x, c.y, c.z, c.w));
         }
     }
+#ifdef SBX_TRACE
+    __syncwarp();
+    if (L.trace != nullptr && lane == 0) {
+        unsigned long long t1;
+        unsigned sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        unsigned long long* rec = L.trace + 4ull * (unsigned long long)trace_warp;
+        rec[0] = trace_t0; rec[1] = t1; rec[2] = sm; rec[3] = coop ? 1u : 0u;
+    }
+#endif
     sbx_signal_done(L);
 }
 

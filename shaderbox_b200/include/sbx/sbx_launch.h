@@ -49,6 +49,9 @@ typedef struct sbx_launch {
     unsigned* done_counter;
     unsigned* done_flag;
     unsigned done_value;
+    /* profiling hook (images built with -DSBX_TRACE only; sbx_set_trace_buffer): warp w of the launch records
+       { start ns, end ns, SM id, region } (4 x u64, %globaltimer) at trace[4 * w] */
+    unsigned long long* trace;
 } sbx_launch;
 
 #endif

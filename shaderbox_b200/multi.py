@@ -107,8 +107,10 @@ class SharedFrame:
     stores on the same NVLink path -- and rank `dst`'s stream waits on the flags with cuStreamWaitValue32
     (sbx_stream_wait_flags).  No collective and no host round trip sits between the last pixel and "frame complete".
 
+    split = "rows": interleaved row stripes (include/sbx.h sbx_shard) -- the default: measured max/mean over 8 ranks
+    1.01 on CLOUDS 1080p, and neighbouring warps stay neighbours in the frame (table lines shared in L1);
     split = "tiles": a checkerboard of 8x4 warp tiles dealt to the ranks (every rank renders the same share of EVERY
-    row: balanced by construction);  split = "rows": interleaved row stripes (include/sbx.h sbx_shard)."""
+    row: balanced by construction, but 3-20 % slower per rank -- a rank's concurrent warps are spread 8 tiles apart)."""
 
     FLAG_BYTES = 4096
 
@@ -138,13 +140,13 @@ class SharedFrame:
         assert self.owner
         return torch.as_tensor(_CudaArray(self.ptr, (self.height, self.width, 4)), device=torch.device("cuda", self.renderer.device))
 
-    def part(self, split="tiles", stripe_rows=DEFAULT_STRIPE_ROWS):
+    def part(self, split="rows", stripe_rows=DEFAULT_STRIPE_ROWS):
         """Keyword arguments of Renderer.render_frame_part for this rank's part of the frame."""
         if split == "tiles":
             return {"shard": None, "tile_parts": self.world, "tile_part": self.rank}
         return {"shard": shard_of(self.rank, self.world, stripe_rows), "tile_parts": 1, "tile_part": 0}
 
-    def launch(self, params, split="tiles", stripe_rows=DEFAULT_STRIPE_ROWS, signal="flags", stream=None):
+    def launch(self, params, split="rows", stripe_rows=DEFAULT_STRIPE_ROWS, signal="flags", stream=None):
         """Enqueue this rank's part of one frame (asynchronous).  With signal="flags" the launch publishes its
         completion flag; complete() on the owner then orders "every part has landed" on its stream."""
         assert params.width == self.width and params.height == self.height
@@ -167,7 +169,7 @@ class SharedFrame:
             # a one-element all-reduce on the launching stream orders "every rank's kernel has finished"
             dist.all_reduce(self._done, group=self.group)
 
-    def render(self, params, stripe_rows=DEFAULT_STRIPE_ROWS, split="tiles", signal="flags"):
+    def render(self, params, stripe_rows=DEFAULT_STRIPE_ROWS, split="rows", signal="flags"):
         """One frame: every rank launches its part into the shared frame; on the owner, work enqueued after this call
         on the current stream sees the complete frame.  (The other ranks do not wait: a caller that re-renders into
         the same frame before the owner has consumed it needs its own ordering -- a barrier, or two frames.)"""
@@ -246,7 +248,7 @@ class SharedHostFrame:
         if self.world > 1:
             dist.barrier(group)
 
-    def render(self, params, stripe_rows=DEFAULT_STRIPE_ROWS, split="tiles"):
+    def render(self, params, stripe_rows=DEFAULT_STRIPE_ROWS, split="rows"):
         """One frame, synchronous: on return (every rank) the frame is complete in host memory (self.array)."""
         assert params.width == self.width and params.height == self.height
         stream = torch.cuda.current_stream(torch.device("cuda", self.renderer.device)).cuda_stream if torch.cuda.is_available() else 0

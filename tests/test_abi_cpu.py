@@ -223,3 +223,31 @@ def test_tile_parts_partition_every_frame(w, h):
             per_row = m.sum(axis=1)
             assert per_row.max() - per_row.min() <= 8 and abs(per_row.mean() - w / parts) <= 8
         assert (total == 1).all()
+
+
+def _build_multi_c(tmp_path):
+    exe = tmp_path / "multi_c"
+    lib_dir = os.path.dirname(sbx.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "tests", "native", "multi_c.c"),
+                    "-o", str(exe), "-L" + lib_dir, "-lsbx", "-Wl,-rpath," + lib_dir], check=True)
+    return exe
+
+
+def test_c_host_of_the_multi_gpu_group_builds_and_refuses_without_a_device(tmp_path):
+    """tests/native/multi_c.c (sbx_multi_* from plain C) compiles as strict C99; without a GPU it reports so and exits 3."""
+    import torch
+
+    exe = _build_multi_c(tmp_path)
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(exe), "2"], capture_output=True, text=True)
+        assert r.returncode == 3 and "no CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("parts", [1, 2, 5, 8])
+def test_c_host_renders_one_frame_over_several_parts(tmp_path, parts):
+    """The C host: one process, `parts` parts (over the GPUs present, shared round-robin), frames byte-identical to 1 GPU."""
+    exe = _build_multi_c(tmp_path)
+    for app in ("APP_CLOUDS", "APP_PLANET"):
+        r = subprocess.run([str(exe), str(parts), app], capture_output=True, text=True)
+        assert r.returncode == 0 and '"ok": true' in r.stdout, r.stdout + r.stderr
