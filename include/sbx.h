@@ -171,6 +171,11 @@ typedef struct sbx_frame_part {
     unsigned done_value;
 } sbx_frame_part;
 int sbx_render_frame_part(sbx_ctx* ctx, const sbx_params* p, const sbx_frame_part* part, float* dev_frame, void* stream);
+/* The same signal from the stream instead of the kernel: after everything enqueued on `stream` so far has completed,
+ * store `value` at dev_flag (cuStreamWriteValue32, preceded by a system-scope fence).  No kernel-side cost; measured on
+ * 8 B200s it is the cheaper of the two when the pixels travel over NVLink (the in-kernel flag makes every thread block
+ * wait for its peer writes to be acknowledged: +7 % kernel time on a 0.36 ms launch), DESIGN.md 7b. */
+int sbx_stream_write_flag(sbx_ctx* ctx, unsigned* dev_flag, unsigned value, void* stream);
 /* Make `stream` wait (on the device, cuStreamWaitValue32) until each of the n flags at dev_flags is >= value. */
 int sbx_stream_wait_flags(sbx_ctx* ctx, const unsigned* dev_flags, int n, unsigned value, void* stream);
 
@@ -256,6 +261,10 @@ int sbx_dds_volume_header(int size, unsigned char* out, int capacity);
  * ships a hybrid image, a launch smaller than M/100 waves of resident warps marches its last T/100 waves' worth of
  * rows with 4 lanes per pixel and the rest with one (measured on B200: it does not beat the whole-launch choice
  * below, DESIGN.md 7b -- the long warps are the ones just above the horizon, not the last ones).
+ * "trivial_rows_last" 0|1 (default 1): issue the rows a kernel image declares trivial (APP_CLOUDS: the sky under the
+ * horizon) at the END of the launch, where they fill the drain instead of delaying the long rays.
+ * "record_events" 0|1 (default 1): bracket render launches with the two timing events behind sbx_last_timing.kernel_ms;
+ * 0 drops them for sbx_render_frame / sbx_render_frame_part (about 2 us of stream time each; kernel_ms then reads 0).
  * "use_hash_table" 0|1, "hash_table_log2" 9..22 (noise_iq memo table), "host_zero_copy" 0|1,
  * "coop_waves_x100" W (default 250): with the default variant, launches smaller than W/100 waves of resident warps
  * use the app's 4-lanes-per-pixel cooperative image, launches smaller than 2W/100 waves the 2-lane one, if

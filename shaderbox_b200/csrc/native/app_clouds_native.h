@@ -38,6 +38,12 @@
 #include "util.h"
 #include "intersect.h"
 
+// Issue-order hint for the launcher (sbx_kernel.cuh, SBX_HINT_TRIVIAL_ROWS is set on the compiler command line from this
+// value, csrc/Makefile): with the camera of setup_camera (:23-30: eye (0,-.5,0) looking at (0,0,-1), yaw only) and FOV 1,
+// a ray's direction has y < 0.05 -- render() returns the sky colour, :212 -- on every pixel of the bottom 25.1 % of the
+// frame (centre column; 28 % at the left and right edges).  250 per mille of the rows are issued last.  A performance
+// hint only: pixels there that do meet cloud (another camera) are marched like any other.
+
 #define hg_g (.2f)
 #include "volumetric.h"
 #include "noise_iq.h"
@@ -87,10 +93,22 @@ SBX_FN float2 sbx_slices(float2 pxy, float pz, float2 wxy) {
                   pk_mix(pk(hi.x, hi.y), pk(hi.z, hi.w), axy.x, wxy.x), axy.y, wxy.y);
 }
 
+// -DSBX_X_FLOOR_MAGIC (experiment, profiles/r02g): floor() without the XU pipe's FRND -- (x + 1.5*2^23) - 1.5*2^23 is x
+// rounded to the nearest integer for |x| < 2^22 (larger lattice coordinates leave the memo table anyway and take the
+// generic path), minus 1 where that rounded up.  Same value as floorf except the sign of a zero result.
+#ifdef SBX_X_FLOOR_MAGIC
+SBX_FN float sbx_floor(float x) {
+    const float n = (x + 12582912.0f) - 12582912.0f;
+    return n > x ? n - 1.0f : n;
+}
+#else
+SBX_FN float sbx_floor(float x) { return floor(x); }
+#endif
+
 // one octave at p = (pxy, pz), evaluated in full; leaves its lattice z and slices in the memo
 SBX_FN float sbx_octave(float2 pxy, float pz, float& mz, float2& ys) {
-    const float2 cxy = pk(floor(pxy.x), floor(pxy.y));
-    const float cz = floor(pz);
+    const float2 cxy = pk(sbx_floor(pxy.x), sbx_floor(pxy.y));
+    const float cz = sbx_floor(pz);
     ys = sbx_slices(cxy, cz, sbx_noise_weight(pk_sub(pxy, cxy)));
     mz = cz;
     return sbx_noise_zmix(ys, sbx_noise_weight(pz - cz));
@@ -156,8 +174,8 @@ template <bool BOUNDED> SBX_FN float illuminate_volume(float2 origin_xy, float o
         const float z0 = pos_z * cld_noise_factor * 2.03f;     // the z chain of p = pos*.001*2.03, p *= 2.64
         const float z1 = z0 * 2.64f, z2 = z1 * 2.64f, z3 = z2 * 2.64f;
         const float2 z01 = pk(z0, z1), z23 = pk(z2, z3);
-        // fract(z) against the memoised lattice z: f = z - m lies in [0, 1) only if floor(z) == m (z < m gives
-        // f < 0, z >= m + 1 gives f >= 1: rounding is monotonic), and then it IS the reference's z - floor(z).
+        // fract(z) against the memoised lattice z: f = z - m lies in [0, 1) only if sbx_floor(z) == m (z < m gives
+        // f < 0, z >= m + 1 gives f >= 1: rounding is monotonic), and then it IS the reference's z - sbx_floor(z).
         // As unsigned integers the floats of [+0, 1) are exactly the values below bits(1.0f).
         float2 f01 = pk_sub(z01, m01), f23 = pk_sub(z23, m23);
         const unsigned worst = ::max(::max(__float_as_uint(f01.x), __float_as_uint(f01.y)),
@@ -165,29 +183,29 @@ template <bool BOUNDED> SBX_FN float illuminate_volume(float2 origin_xy, float o
         const bool same_xy = pos_xy.x == sbx_mx && pos_xy.y == sbx_my;
         if (!(same_xy && worst < 0x3f800000u)) {
             // re-slice the octaves that left their cell (all of them if x or y changed)
-            const float2 c01 = pk(floor(z0), floor(z1)), c23 = pk(floor(z2), floor(z3));
+            const float2 c01 = pk(sbx_floor(z0), sbx_floor(z1)), c23 = pk(sbx_floor(z2), sbx_floor(z3));
             float2 pxy = pk_mul(pk_mul(pos_xy, cld_noise_factor), 2.03f);
             float2 cxy;
             if (!(same_xy && c01.x == m01.x)) {
-                cxy = pk(floor(pxy.x), floor(pxy.y));
+                cxy = pk(sbx_floor(pxy.x), sbx_floor(pxy.y));
                 ys0 = sbx_slices(cxy, c01.x, sbx_noise_weight(pk_sub(pxy, cxy)));
                 m01.x = c01.x;
             }
             pxy = pk_mul(pxy, 2.64f);
             if (!(same_xy && c01.y == m01.y)) {
-                cxy = pk(floor(pxy.x), floor(pxy.y));
+                cxy = pk(sbx_floor(pxy.x), sbx_floor(pxy.y));
                 ys1 = sbx_slices(cxy, c01.y, sbx_noise_weight(pk_sub(pxy, cxy)));
                 m01.y = c01.y;
             }
             pxy = pk_mul(pxy, 2.64f);
             if (!(same_xy && c23.x == m23.x)) {
-                cxy = pk(floor(pxy.x), floor(pxy.y));
+                cxy = pk(sbx_floor(pxy.x), sbx_floor(pxy.y));
                 ys2 = sbx_slices(cxy, c23.x, sbx_noise_weight(pk_sub(pxy, cxy)));
                 m23.x = c23.x;
             }
             pxy = pk_mul(pxy, 2.64f);
             if (!(same_xy && c23.y == m23.y)) {
-                cxy = pk(floor(pxy.x), floor(pxy.y));
+                cxy = pk(sbx_floor(pxy.x), sbx_floor(pxy.y));
                 ys3 = sbx_slices(cxy, c23.y, sbx_noise_weight(pk_sub(pxy, cxy)));
                 m23.y = c23.y;
             }

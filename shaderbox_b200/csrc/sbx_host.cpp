@@ -87,6 +87,8 @@ sbx::driver_api* sbx::load_driver(std::string* err) {
     SBX_SYM(MemHostAlloc, "cuMemHostAlloc")
     SBX_SYM(MemFreeHost, "cuMemFreeHost")
     SBX_SYM(StreamWaitValue32, "cuStreamWaitValue32_v2")
+    SBX_SYM(StreamWriteValue32, "cuStreamWriteValue32_v2")
+    SBX_SYM(StreamBatchMemOp, "cuStreamBatchMemOp_v2")
     SBX_SYM(StreamWaitEvent, "cuStreamWaitEvent")
     SBX_SYM(StreamCreate, "cuStreamCreate")
     SBX_SYM(StreamDestroy, "cuStreamDestroy_v2")
@@ -110,6 +112,7 @@ struct kernel_image {
     int warps_per_cta = 4;
     int tile_w = SBX_TILE_W, tile_h = SBX_TILE_H, lanes_per_pixel = 1;   // sbx_image_info of the image
     int hybrid_lanes = 0;         // > 1: the image has a second region marched with this many lanes per pixel
+    int trivial_rows_permille = 0;   // sbx_image_hints[0]: this share of the frame's bottom rows is trivial (issued last)
     std::string variant;
 };
 
@@ -150,6 +153,8 @@ struct sbx_ctx {
     int opt_use_hash = 1;
     int opt_zero_copy = 1;        // sbx_render_host: store straight into pinned+mapped host frames
     int opt_coop_waves_x100 = 250;   // use the cooperative image when the grid is below this many waves of resident warps
+    int opt_trivial_rows_last = 1;   // honour sbx_image_hints[0]
+    int opt_record_events = 1;       // bracket every render launch with timing events (sbx_last_timing.kernel_ms)
     int opt_tail_waves_x100 = 0;     // hybrid image (opt-in): march the last this-many waves of the launch with 4 lanes per pixel
     int opt_tail_max_waves_x100 = 1200;  // ... for launches below this many waves (a long launch amortises its tail anyway)
     CUdeviceptr trace = 0;           // profiling hook: per-warp records of the next launches (trace images only)
@@ -265,6 +270,14 @@ int bind_image(sbx_ctx* ctx, const std::string& key, const std::string& cubin, c
             ctx->cu->MemcpyDtoH(v, info, sizeof v) == CUDA_SUCCESS && v[0] > 0 && v[1] > 0 && v[2] > 0) {
             img.tile_w = v[0]; img.tile_h = v[1]; img.lanes_per_pixel = v[2]; img.hybrid_lanes = v[3] > 1 ? v[3] : 0;
         }
+    }
+    {
+        CUdeviceptr hints = 0;
+        size_t bytes = 0;
+        int v[4] = {0, 0, 0, 0};
+        if (ctx->cu->ModuleGetGlobal(&hints, &bytes, img.module, "sbx_image_hints") == CUDA_SUCCESS && bytes >= sizeof v &&
+            ctx->cu->MemcpyDtoH(v, hints, sizeof v) == CUDA_SUCCESS && v[0] > 0 && v[0] < 1000)
+            img.trivial_rows_permille = v[0];
     }
     auto it = ctx->images.find(key);
     if (it != ctx->images.end() && it->second.module) ctx->cu->ModuleUnload(it->second.module);
@@ -502,6 +515,8 @@ int sbx_set_option(sbx_ctx* ctx, const char* key, int value) {
     if (!std::strcmp(key, "use_hash_table")) { ctx->opt_use_hash = value ? 1 : 0; return SBX_OK; }
     if (!std::strcmp(key, "host_zero_copy")) { ctx->opt_zero_copy = value ? 1 : 0; return SBX_OK; }
     if (!std::strcmp(key, "coop_waves_x100")) { if (value < 0) return SBX_ERR_INVALID; ctx->opt_coop_waves_x100 = value; return SBX_OK; }
+    if (!std::strcmp(key, "trivial_rows_last")) { ctx->opt_trivial_rows_last = value ? 1 : 0; return SBX_OK; }
+    if (!std::strcmp(key, "record_events")) { ctx->opt_record_events = value ? 1 : 0; return SBX_OK; }
     if (!std::strcmp(key, "tail_waves_x100")) { if (value < 0) return SBX_ERR_INVALID; ctx->opt_tail_waves_x100 = value; return SBX_OK; }
     if (!std::strcmp(key, "tail_max_waves_x100")) { if (value < 0) return SBX_ERR_INVALID; ctx->opt_tail_max_waves_x100 = value; return SBX_OK; }
     return SBX_ERR_INVALID;
@@ -518,12 +533,15 @@ struct launch_job {
     unsigned done_value = 0;
 };
 
-static void plan_region(sbx_region* r, int width, int tile_w, int tile_h, int col_parts, int row0, int rows, int warps_per_cta) {
+static void plan_region(sbx_region* r, int width, int tile_w, int tile_h, int col_parts, int row0, int rows, int warps_per_cta,
+                        int first_row = 0) {
     const int tiles_x = (width + tile_w - 1) / tile_w;
+    r->first_tile_row = rows > 0 ? (first_row / tile_h) % ((rows + tile_h - 1) / tile_h) : 0;
     r->tiles_per_row = col_parts > 1 ? (tiles_x + col_parts - 1) / col_parts : tiles_x;
     r->row0 = row0;
     r->rows = rows;
-    r->warps = ((rows + tile_h - 1) / tile_h) * r->tiles_per_row;
+    r->tile_rows = (rows + tile_h - 1) / tile_h;
+    r->warps = r->tile_rows * r->tiles_per_row;
     // the grid is rounded up to whole CTAs: the largest warp index is < warps + warps_per_cta
     const unsigned long long nmax = (unsigned long long)r->warps + (unsigned long long)warps_per_cta;
     r->magic = (r->tiles_per_row > 0 && nmax * (unsigned long long)r->tiles_per_row < (1ull << 40))
@@ -583,7 +601,11 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const launch_job& jo
     // hybrid) cuts the same parts; the 2-lane image (16-wide tiles) would not
     if (job.col_parts > 1 && img->tile_w != SBX_TILE_W) { img = ctx->current; rows_tail = 0; }
     if (L.local_rows > 0) {
-        plan_region(&L.reg[0], p->width, img->tile_w, img->tile_h, job.col_parts, 0, L.local_rows - rows_tail, img->warps_per_cta);
+        // rows the image declares trivial (a share of the frame's bottom) go last: the launch starts at this shard's first
+        // row at or above that frame row -- counted in FRAME rows, so every part of a striped frame starts on the same line
+        const int first_row = ctx->opt_trivial_rows_last && rows_tail == 0 && img->trivial_rows_permille > 0
+                                  ? shard_rows(s, (int)((long long)p->height * img->trivial_rows_permille / 1000)) : 0;
+        plan_region(&L.reg[0], p->width, img->tile_w, img->tile_h, job.col_parts, 0, L.local_rows - rows_tail, img->warps_per_cta, first_row);
         if (rows_tail > 0)
             plan_region(&L.reg[1], p->width, 32 / img->hybrid_lanes, 1, job.col_parts, L.local_rows - rows_tail, rows_tail, img->warps_per_cta);
     }
@@ -612,11 +634,13 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const launch_job& jo
     if (warps == 0 && !job.done_flag) return SBX_OK;
     const unsigned grid = (unsigned)std::max<long long>(1, (warps + img->warps_per_cta - 1) / img->warps_per_cta);
     void* args[] = {&L};
-    SBX_TRY(ctx->cu->EventRecord(ctx->ev0, stream), "cuEventRecord");
+    // the two timing events cost ~2 us of stream time each: a caller that times its own launches switches them off
+    const bool timed = ctx->opt_record_events || !job.out_is_frame;
+    if (timed) SBX_TRY(ctx->cu->EventRecord(ctx->ev0, stream), "cuEventRecord");
     SBX_TRY(ctx->cu->LaunchKernel(img->render, grid, (unsigned)n_frames, 1, (unsigned)img->warps_per_cta * 32, 1, 1,
                                   SBX_LUT_MATH_BYTES, stream, args, nullptr),
             "launch sbx_render");
-    SBX_TRY(ctx->cu->EventRecord(ctx->ev1, stream), "cuEventRecord");
+    if (timed) SBX_TRY(ctx->cu->EventRecord(ctx->ev1, stream), "cuEventRecord");
     ctx->timing.launches += 1;
     ctx->timing.grid_blocks = (int)grid;
     ctx->timing.block_threads = img->warps_per_cta * 32;
@@ -625,7 +649,7 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const launch_job& jo
     ctx->timing.lanes_per_pixel = img->lanes_per_pixel;
     ctx->timing.tail_rows = rows_tail;
     ctx->timing.tail_lanes_per_pixel = rows_tail > 0 ? img->hybrid_lanes : 0;
-    ctx->timing.kernel_ms = -1.0f;   // resolved lazily by sbx_last_timing
+    ctx->timing.kernel_ms = timed ? -1.0f : 0.0f;   // -1: resolved lazily by sbx_last_timing
     ctx->timing.d2h_ms = 0.0f;
     return SBX_OK;
 }
@@ -738,10 +762,28 @@ int sbx_render_frame_part(sbx_ctx* ctx, const sbx_params* p, const sbx_frame_par
 
 int sbx_stream_wait_flags(sbx_ctx* ctx, const unsigned* dev_flags, int n, unsigned value, void* stream) {
     if (!ctx || !dev_flags || n < 0) return SBX_ERR_INVALID;
+    if (n == 0) return SBX_OK;
+    if (n > 256) return ctx->fail(SBX_ERR_INVALID, "at most 256 flags per wait");
     ctx_scope scope(ctx);
-    for (int i = 0; i < n; ++i)
-        SBX_TRY(ctx->cu->StreamWaitValue32((CUstream)stream, (CUdeviceptr)(uintptr_t)(dev_flags + i), value, CU_STREAM_WAIT_VALUE_GEQ),
-                "cuStreamWaitValue32");
+    // one submission for all n waits (cuStreamBatchMemOp)
+    CUstreamBatchMemOpParams ops[256];
+    std::memset(ops, 0, sizeof(ops[0]) * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        ops[i].waitValue.operation = CU_STREAM_MEM_OP_WAIT_VALUE_32;
+        ops[i].waitValue.address = (CUdeviceptr)(uintptr_t)(dev_flags + i);
+        ops[i].waitValue.value = value;
+        ops[i].waitValue.flags = CU_STREAM_WAIT_VALUE_GEQ;
+    }
+    SBX_TRY(ctx->cu->StreamBatchMemOp((CUstream)stream, (unsigned)n, ops, 0), "cuStreamBatchMemOp(wait flags)");
+    return SBX_OK;
+}
+
+int sbx_stream_write_flag(sbx_ctx* ctx, unsigned* dev_flag, unsigned value, void* stream) {
+    if (!ctx || !dev_flag) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    // default flags: the write is preceded by a system-scope fence over the stream's earlier work
+    SBX_TRY(ctx->cu->StreamWriteValue32((CUstream)stream, (CUdeviceptr)(uintptr_t)dev_flag, value, CU_STREAM_WRITE_VALUE_DEFAULT),
+            "cuStreamWriteValue32");
     return SBX_OK;
 }
 

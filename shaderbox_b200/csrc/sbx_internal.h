@@ -52,6 +52,8 @@ struct driver_api {
     CUresult (*MemHostAlloc)(void**, size_t, unsigned);
     CUresult (*MemFreeHost)(void*);
     CUresult (*StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned);
+    CUresult (*StreamWriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned);
+    CUresult (*StreamBatchMemOp)(CUstream, unsigned, CUstreamBatchMemOpParams*, unsigned);
     CUresult (*StreamWaitEvent)(CUstream, CUevent, unsigned);
     CUresult (*StreamCreate)(CUstream*, unsigned);
     CUresult (*StreamDestroy)(CUstream);

@@ -8,9 +8,9 @@
 // dealt round-robin, sbx_frame_part -- straight into the destination:
 //   sbx_multi_render_device  the group's frame in the first GPU's HBM: peers store over NVLink, the first GPU's
 //                            stream waits for every part with cross-device events (no collective)
-//   sbx_multi_render_host    a pinned host frame (sbx_host_alloc): every GPU stores over its own PCIe link and
-//                            publishes a completion flag in pinned memory that the caller polls; a pageable frame is
-//                            rendered in HBM as above and copied
+//   sbx_multi_render_host    a pinned host frame (sbx_host_alloc): every GPU stores over its own PCIe link and its
+//                            stream publishes a completion flag in pinned memory (cuStreamWriteValue32) that the
+//                            caller polls; a pageable frame is rendered in HBM as above and copied
 // Pixels are independent (src/main.h:6-53), so the assembled frame is bit-identical to a 1-GPU render.
 #include <atomic>
 #include <chrono>
@@ -73,12 +73,14 @@ int run_part(sbx_multi* m, int i) {
     part.rows.stripe_rows = 4; part.rows.n_parts = m->n; part.rows.part = i;
     part.tile_parts = 1;
     part.tile_part = 0;
-    part.done_flag = t.flag ? t.flag + i : nullptr;
-    part.done_value = t.value;
+    part.done_flag = nullptr;
+    part.done_value = 0;
     scope s(m->cu, sbx::context_of(m->ctx[i]));
     if (i > 0 && m->cu->StreamWaitEvent(m->stream[i], m->start, 0) != CUDA_SUCCESS) return SBX_ERR_CUDA;
-    const int st = sbx_render_frame_part(m->ctx[i], t.p, &part, t.dest, m->stream[i]);
+    int st = sbx_render_frame_part(m->ctx[i], t.p, &part, t.dest, m->stream[i]);
     if (st != SBX_OK) return st;
+    // host frames: the stream publishes "this part has landed" in pinned memory behind the launch
+    if (t.flag && (st = sbx_stream_write_flag(m->ctx[i], t.flag + i, t.value, m->stream[i])) != SBX_OK) return st;
     if (m->cu->EventRecord(m->done[i], m->stream[i]) != CUDA_SUCCESS) return SBX_ERR_CUDA;
     return SBX_OK;
 }
@@ -263,8 +265,8 @@ int sbx_multi_render_host(sbx_multi* m, const sbx_params* p, float* host_rgba) {
             m->cu->PointerGetAttribute(&alias, CU_POINTER_ATTRIBUTE_DEVICE_POINTER, (CUdeviceptr)(uintptr_t)host_rgba);
     }
     if (alias) {
-        // pinned + mapped frame: every GPU stores its part over its own PCIe link, then its last thread block
-        // publishes the frame number in pinned memory; the caller polls the N words
+        // pinned + mapped frame: every GPU stores its part over its own PCIe link, then its stream publishes the
+        // frame number in pinned memory; the caller polls the N words
         sbx_multi::task t;
         t.p = p;
         t.dest = (float*)(uintptr_t)alias;

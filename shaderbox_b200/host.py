@@ -56,6 +56,7 @@ def lib():
         L.sbx_render_frame.argtypes = [C.c_void_p, P(Params), P(Shard), C.c_void_p, C.c_void_p]
         L.sbx_render_frame_part.argtypes = [C.c_void_p, P(Params), P(FramePart), C.c_void_p, C.c_void_p]
         L.sbx_stream_wait_flags.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_void_p]
+        L.sbx_stream_write_flag.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
         L.sbx_host_alloc.argtypes = [C.c_void_p, C.c_size_t, P(C.c_void_p)]
         L.sbx_host_free.argtypes = [C.c_void_p, C.c_void_p]
         L.sbx_multi_create.argtypes = [P(C.c_int), C.c_int, P(C.c_void_p)]
@@ -105,7 +106,7 @@ EXPORTS = (
     "sbx_render_frame_part", "sbx_stream_wait_flags", "sbx_host_alloc", "sbx_host_free",
     "sbx_multi_create", "sbx_multi_destroy", "sbx_multi_gpus", "sbx_multi_ctx", "sbx_multi_load_app", "sbx_multi_set_option",
     "sbx_multi_render_device", "sbx_multi_render_host", "sbx_multi_stream", "sbx_multi_sync", "sbx_multi_last_timing",
-    "sbx_multi_last_error", "sbx_device_count", "sbx_set_trace_buffer",
+    "sbx_multi_last_error", "sbx_device_count", "sbx_set_trace_buffer", "sbx_stream_write_flag",
 )
 
 
@@ -236,6 +237,11 @@ class Renderer:
                          C.c_void_p(done_flag or None), int(done_value))
         self._check(self._L.sbx_render_frame_part(self._ctx, C.byref(params), C.byref(part), C.c_void_p(dev_frame_ptr),
                                                   C.c_void_p(stream)), "sbx_render_frame_part")
+
+    def stream_write_flag(self, dev_flag_ptr, value, stream=0):
+        """After the work enqueued on `stream` so far: store `value` at the 32-bit flag (own, peer or mapped host memory)."""
+        self._check(self._L.sbx_stream_write_flag(self._ctx, C.c_void_p(dev_flag_ptr), int(value), C.c_void_p(stream)),
+                    "sbx_stream_write_flag")
 
     def stream_wait_flags(self, dev_flags_ptr, n, value, stream=0):
         """Stream-ordered wait (on the device) until each of the n 32-bit flags at `dev_flags_ptr` is >= value."""

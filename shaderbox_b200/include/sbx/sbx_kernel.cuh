@@ -51,6 +51,13 @@
 extern "C" __device__ const int sbx_image_info[4] = {SBX_IMG_TILE_W, SBX_IMG_TILE_H, SBX_LANES_PER_PIXEL,
                                                      SBX_HYBRID_LANES > 1 ? SBX_HYBRID_LANES : 0};
 
+// read by the host at load time: { per-mille of the frame height, from the bottom, whose pixels are known to be trivial
+// (they return before any march) -- the launch issues those rows LAST; 0, 0, 0 }.  A scene kernel sets SBX_HINT_TRIVIAL_ROWS.
+#ifndef SBX_HINT_TRIVIAL_ROWS
+#define SBX_HINT_TRIVIAL_ROWS 0
+#endif
+extern "C" __device__ const int sbx_image_hints[4] = {SBX_HINT_TRIVIAL_ROWS, 0, 0, 0};
+
 // ---- TMA bulk copy of the LUT block: global -> shared, completion on an mbarrier --------------
 __device__ __forceinline__ unsigned sbx_smem_addr(const void* p) {
     return (unsigned)__cvta_generic_to_shared(p);
@@ -132,8 +139,30 @@ __device__ __forceinline__ void sbx_signal_done(const sbx_launch& L) {
     }
 }
 
+// The first SBX_PREFETCH_CTAS thread blocks of a launch each ask the L2 for one slice of the lattice-hash memo table
+// (cp.async.bulk.prefetch.L2: one instruction, no completion to wait for).  After an L2 flush -- or on the first frame --
+// the table's lines would otherwise arrive one dependent miss at a time (octave after octave, ~0.7 us each from HBM);
+// the whole 8 MB is 1.3 us of HBM bandwidth.
+#ifndef SBX_PREFETCH_CTAS
+#define SBX_PREFETCH_CTAS 128
+#endif
+__device__ __forceinline__ void sbx_prefetch_tables(const sbx_launch& L) {
+#if SBX_PREFETCH_CTAS > 0
+    if (threadIdx.x == 32 && blockIdx.x < SBX_PREFETCH_CTAS && blockIdx.y == 0 && L.hash_len > 0) {
+        const unsigned long long total = (unsigned long long)L.hash_len * 32ull;               // bytes (a multiple of 16 KB)
+        const unsigned long long slice = (total / SBX_PREFETCH_CTAS + 15ull) & ~15ull;
+        const unsigned long long at = slice * blockIdx.x;
+        if (at < total) {
+            const unsigned bytes = (unsigned)(total - at < slice ? total - at : slice);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(L.hash_tab) + at), "r"(bytes) : "memory");
+        }
+    }
+#endif
+}
+
 extern "C" __global__ void __launch_bounds__(SBX_WARPS_PER_CTA * 32, SBX_MIN_CTAS_PER_SM)
 sbx_render(const __grid_constant__ sbx_launch L) {
+    sbx_prefetch_tables(L);
     sbx_stage_lut(L.lut);
 
     int warp = blockIdx.x * SBX_WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -158,8 +187,14 @@ sbx_render(const __grid_constant__ sbx_launch L) {
 #endif
     const int tile_w = P == 1 ? SBX_TILE_W : 32 / P, tile_h = P == 1 ? SBX_TILE_H : 1;
     // warp -> (tile row, column slot): division by the host's magic number (0 = divide)
-    const int trow = R.magic ? (int)(((unsigned long long)(unsigned)warp * R.magic) >> 40) : warp / R.tiles_per_row;
+    int trow = R.magic ? (int)(((unsigned long long)(unsigned)warp * R.magic) >> 40) : warp / R.tiles_per_row;
     int tile_x = warp - trow * R.tiles_per_row;
+    // issue order: tile rows from first_tile_row upwards, then the ones below it (an app whose bottom rows are trivial --
+    // APP_CLOUDS' sky under the horizon -- says so in sbx_image_hints, and those rows then fill the end of the launch)
+    if (warp < R.warps) {
+        trow += R.first_tile_row;
+        trow -= trow >= R.tile_rows ? R.tile_rows : 0;
+    }
     const int lr0 = R.row0 + trow * tile_h;
     if (L.col_parts > 1) {   // this part's columns of the row: (tile_x + lr0 / 4) % col_parts == col_part
         int first = (L.col_part - (lr0 >> 2)) % L.col_parts;

@@ -17,6 +17,8 @@ typedef struct sbx_region {
     int warps;                  /* tile rows * tiles_per_row */
     int tiles_per_row;          /* column slots per tile row (this part's share of the tile columns, rounded up) */
     int row0, rows;             /* local rows [row0, row0 + rows) */
+    int tile_rows;              /* warps / tiles_per_row */
+    int first_tile_row;         /* tile rows are ISSUED starting here and wrapping round (the rows below it go last) */
     unsigned long long magic;   /* ceil(2^40 / tiles_per_row) when warps * tiles_per_row < 2^40, else 0 (kernel divides) */
 } sbx_region;
 

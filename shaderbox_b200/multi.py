@@ -102,10 +102,11 @@ class SharedFrame:
     (sbx_frame_alloc / sbx_frame_export / sbx_frame_import), so each rank's render kernel stores its
     part straight into it over NVLink: the gather is fused into the render kernel.
 
-    Behind the frame sit `world` 32-bit completion flags (same allocation, so the same IPC mapping): the last thread
-    block of rank r's launch stores the frame number into flag r -- in rank `dst`'s memory, right behind its own pixel
-    stores on the same NVLink path -- and rank `dst`'s stream waits on the flags with cuStreamWaitValue32
-    (sbx_stream_wait_flags).  No collective and no host round trip sits between the last pixel and "frame complete".
+    Behind the frame sit `world` 32-bit completion flags (same allocation, so the same IPC mapping): when rank r's
+    launch has finished, its stream stores the frame number into flag r -- in rank `dst`'s memory, over the same
+    NVLink path as its pixels (sbx_stream_write_flag; signal="kernel": the launch's last thread block stores it
+    instead) -- and rank `dst`'s stream waits on the flags with cuStreamWaitValue32 (sbx_stream_wait_flags).  No
+    collective and no host round trip sits between the last pixel and "frame complete".
 
     split = "rows": interleaved row stripes (include/sbx.h sbx_shard) -- the default: measured max/mean over 8 ranks
     1.01 on CLOUDS 1080p, and neighbouring warps stay neighbours in the frame (table lines shared in L1);
@@ -153,14 +154,16 @@ class SharedFrame:
         if stream is None:
             stream = torch.cuda.current_stream(torch.device("cuda", self.renderer.device)).cuda_stream
         self.epoch += 1
-        flag = self.flags_ptr + 4 * self.rank if (signal == "flags" and self.world > 1) else 0
-        self.renderer.render_frame_part(params, self.ptr, done_flag=flag, done_value=self.epoch, stream=stream,
-                                        **self.part(split, stripe_rows))
+        flag = self.flags_ptr + 4 * self.rank if self.world > 1 else 0
+        self.renderer.render_frame_part(params, self.ptr, done_flag=flag if signal == "kernel" else 0, done_value=self.epoch,
+                                        stream=stream, **self.part(split, stripe_rows))
+        if signal == "flags" and flag:
+            self.renderer.stream_write_flag(flag, self.epoch, stream=stream)
 
     def complete(self, signal="flags", stream=None):
         if self.world == 1:
             return
-        if signal == "flags":
+        if signal in ("flags", "kernel"):
             if self.owner:
                 if stream is None:
                     stream = torch.cuda.current_stream(torch.device("cuda", self.renderer.device)).cuda_stream
@@ -193,10 +196,10 @@ class SharedHostFrame:
     part straight into it over its own PCIe link.  This is the end-to-end path of an N-GPU host: no gather to one
     GPU, no device->host copy of the assembled frame.
 
-    Completion: behind the frame sits a control page with one 32-bit slot per rank.  The last thread block of rank r's
-    launch stores the frame number into slot r (sbx_frame_part.done_flag: a system-scope release store issued after a
-    system-scope fence over the launch's pixel stores, travelling the same PCIe path behind them), and every rank's
-    host thread polls the slots until all show the frame number -- no stream synchronise, no collective."""
+    Completion: behind the frame sits a control page with one 32-bit slot per rank.  When rank r's launch has finished,
+    its stream stores the frame number into slot r (sbx_stream_write_flag: cuStreamWriteValue32 behind a system-scope
+    fence, travelling the same PCIe path as the pixels), and every rank's host thread polls the slots until all show
+    the frame number -- no stream synchronise, no collective."""
 
     def __init__(self, renderer, width, height, dst=0, group=None):
         import mmap
@@ -255,8 +258,8 @@ class SharedHostFrame:
         self._epoch += 1
         part = ({"shard": None, "tile_parts": self.world, "tile_part": self.rank} if split == "tiles" else
                 {"shard": shard_of(self.rank, self.world, stripe_rows), "tile_parts": 1, "tile_part": 0})
-        self.renderer.render_frame_part(params, self.alias, done_flag=self.slots_alias + 4 * self.rank, done_value=self._epoch,
-                                        stream=stream, **part)
+        self.renderer.render_frame_part(params, self.alias, stream=stream, **part)
+        self.renderer.stream_write_flag(self.slots_alias + 4 * self.rank, self._epoch, stream=stream)
         slots, epoch = self._slots, self._epoch
         t_wait = time.monotonic()
         spins = 0

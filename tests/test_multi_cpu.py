@@ -98,6 +98,11 @@ class _OracleHostRenderer:
         if done_flag:           # what the launch's last thread block does after its pixel stores
             ctypes.c_uint.from_address(done_flag).value = done_value
 
+    def stream_write_flag(self, flag, value, stream=0):   # what the stream does behind the launch
+        import ctypes
+
+        ctypes.c_uint.from_address(flag).value = value
+
 
 def _host_frame_worker(rank, world, port, stripe, split, result_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"

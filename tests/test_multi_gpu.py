@@ -39,7 +39,7 @@ def _worker(rank, world, port, out_dir):
         # path 2: every rank's kernel stores into rank 0's frame over NVLink (CUDA IPC mapping)
         shared = multi.SharedFrame(r, W, H)
         for name, kw in (("p2p4", {"split": "rows", "stripe_rows": 4, "signal": "nccl"}),
-                         ("p2p1", {"split": "rows", "stripe_rows": 1, "signal": "flags"}),
+                         ("p2p1", {"split": "rows", "stripe_rows": 1, "signal": "kernel"}),
                          ("tiles", {"split": "tiles", "signal": "flags"}),
                          ("tiles2", {"split": "tiles", "signal": "flags"})):      # a second frame: the flags count frames
             if rank == 0:

@@ -1,0 +1,8 @@
+#!/bin/bash
+# round 2, visit j (1 GPU): whole suite after the issue-order hint; part times with / without it; launch floor with / without events
+OUT=gpurun_out/r02j; mkdir -p $OUT
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 | tee $OUT/pytest_gpu.txt
+timeout 600 python tools/part_time.py clouds1080 8 --variants native,coop,coop2 --splits rows4 --out $OUT/parts_n8.json 2>&1 | tee $OUT/parts_n8.txt
+timeout 600 python tools/part_time.py clouds1080 4 --variants native,coop,coop2 --splits rows4 --out $OUT/parts_n4.json 2>&1 | tee $OUT/parts_n4.txt
+timeout 600 python tools/part_time.py clouds1080 1 --variants native,coop --splits rows4 --out $OUT/parts_n1.json 2>&1 | tee $OUT/parts_n1.txt
+echo done

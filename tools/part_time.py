@@ -48,10 +48,15 @@ def timed(fn, reps=7, do_flush=True):
 results = {}
 r = sbx.Renderer(app, variant="native" if app in ("APP_CLOUDS", "APP_PLANET", "APP_RAYTRACER") else None)
 full_ms = timed(lambda: r.render_frame_part(p, frame.data_ptr(), stream=s.cuda_stream))
-tiny = default_params(8, 4, t, **ov)
-fixed_flush = timed(lambda: r.render_frame_part(tiny, frame.data_ptr(), stream=s.cuda_stream), reps=15)
-fixed_warm = timed(lambda: r.render_frame_part(tiny, frame.data_ptr(), stream=s.cuda_stream), reps=15, do_flush=False)
-print("%s: whole frame %.4f ms -> ideal 1/%d = %.4f ms;  an 8x4-pixel launch between events: %.1f us after an L2 flush, %.1f us warm" % (
+tiny = default_params(8, 4, t)
+rt = sbx.Renderer("APP_RAYTRACER")          # one warp of a cheap app: what a launch costs between two events
+with_events = timed(lambda: rt.render_frame_part(tiny, frame.data_ptr(), stream=s.cuda_stream), reps=15)
+rt.set_option("record_events", 0)
+print("one-warp launch with the context's own timing events: %.1f us; without (below): " % (with_events * 1e3), end="")
+fixed_flush = timed(lambda: rt.render_frame_part(tiny, frame.data_ptr(), stream=s.cuda_stream), reps=15)
+fixed_warm = timed(lambda: rt.render_frame_part(tiny, frame.data_ptr(), stream=s.cuda_stream), reps=15, do_flush=False)
+rt.close()
+print("%s: whole frame %.4f ms -> ideal 1/%d = %.4f ms;  a one-warp RAYTRACER launch between events: %.1f us after an L2 flush, %.1f us warm" % (
     wl, full_ms, parts, full_ms / parts, fixed_flush * 1e3, fixed_warm * 1e3), flush=True)
 results["full_ms"], results["fixed_us_flush"], results["fixed_us_warm"] = full_ms, fixed_flush * 1e3, fixed_warm * 1e3
 r.close()
@@ -60,6 +65,7 @@ for variant in variants:
     for split in splits:
         for tail in (tails if variant == "default" else [0]):
             r = sbx.Renderer(app, variant=None if variant == "default" else variant)
+            r.set_option("record_events", 0)
             if variant == "default":
                 r.set_option("tail_waves_x100", tail)
                 r.set_option("tail_max_waves_x100", 10 ** 6)
