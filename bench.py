@@ -497,8 +497,8 @@ def run_ours(args):
             "e2e": {"value": px * args.steps / e2e_s * 1e-6, "unit": "Mpixels/s", "h2d_bytes_per_step": sbx_params_bytes(),
                     "d2h_bytes_per_step": int(16 * px), "d2h_bytes_per_step_this_rank": int(16 * px / world), "checksum": e2e_sum,
                     "api": ("sbx_render_host (C ABI) into a frame from sbx_host_alloc (pinned + mapped: what INTEGRATION.md tells a host to use)" if world == 1 else
-                            "sbx_render_frame_part on every rank into one shared host frame (sbx_host_frame_register); each launch publishes a completion "
-                            "flag in the frame's control page, every rank's host polls the %d flags" % world),
+                            "sbx_render_frame_part on every rank into one shared host frame (sbx_host_frame_register); each rank's stream publishes a "
+                            "completion flag in the frame's control page behind its launch, every rank's host polls the %d flags" % world),
                     "d2h": "kernel stores straight into the pinned+mapped host frame (zero-copy over PCIe)" if zero_copy
                            else "frame assembled in HBM, then one async copy to host memory",
                     "loop": "back-to-back synchronous calls, wall clock; NO L2 flush and no per-step barrier (unlike `value`), so the two are not like for like"},
