@@ -48,6 +48,8 @@ WORKLOADS = {
     "egg256": ("APP_EGG", 256, 256, 1.0, {}),
     "vinyl1080": ("APP_VINYL", 1920, 1080, 1.25, {}),
     "sdf_ao1080": ("APP_SDF_AO", 1920, 1080, 0.5, {}),
+    # the USE_NOISE_TEX cloud path (two 128^3 noise textures, software D3D11 sampler, TMA-staged texel boxes)
+    "clouds_tex1080": ("APP_CLOUDS_TEX", 1920, 1080, 1.5, {"cld_march_steps": 128}),
 }
 METRIC = "Mpixels/sec at 1920x1080 (APP_CLOUDS)"
 # FP32 lane-instruction cost table for the algorithmic-work estimate (DESIGN.md "Roofline"):
@@ -206,7 +208,7 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
-EXTRA_WORKLOADS = ("atmosphere1080", "planet2160", "raytracer4320")   # BASELINE.json configs[2..4]
+EXTRA_WORKLOADS = ("atmosphere1080", "planet2160", "raytracer4320", "clouds_tex1080")   # BASELINE.json configs[2..4] + SURVEY f3
 
 
 def frame_digest(frame_t):
@@ -239,6 +241,13 @@ class Job:
         self.app, self.w, self.h, self.t, self.ov = WORKLOADS[workload]
         self.p = default_params(self.w, self.h, self.t, **self.ov)
         self.r = sbx.Renderer(self.app, device=env.local_rank, variant=variant)
+        if self.app == "APP_CLOUDS_TEX":
+            # texture 0: the ddsvolgen volume baked on this GPU; texture 1: the same volume mirrored in z (synthetic: the
+            # reference ships no textures)
+            import numpy as np
+
+            vol = self.r.bake_noise_volume(128)
+            self.r.set_noise_volumes(vol, np.ascontiguousarray(vol[::-1]))
         self.shared = multi.SharedFrame(self.r, self.w, self.h)          # world 1: a plain frame on this GPU
         self.stream = torch.cuda.current_stream(env.dev)
         self.px = self.w * self.h

@@ -257,6 +257,16 @@ int sbx_bake_noise_volume_device(sbx_ctx* ctx, int size, int z0, int nz, float* 
 int sbx_bake_noise_volume_host(sbx_ctx* ctx, int size, int z0, int nz, float* host_rgba);
 int sbx_dds_volume_header(int size, unsigned char* out, int capacity);
 
+/* The two 3-D noise textures of the USE_NOISE_TEX cloud path (`Texture3D u_tex_noise, u_tex_noise_2`,
+ * src/app_clouds.h:51-55, bound by hlsltoy from its DDS arguments, util/hlsltoy/src/hlsltoy.cpp:225-239), for the app
+ * "APP_CLOUDS_TEX": that branch of app_clouds.h with `SampleLevel(u_sampler0, pos, 0).r` (:69, :77) evaluated by a
+ * software sampler -- D3D11 linear filtering, WRAP addressing (hlsltoy.cpp:244-249), 8-bit sub-texel weights; the rule is
+ * written down in oracle/sbx_oracle.c and is this library's definition (the reference has no C++ statement of it).
+ * Volumes are size^3 R32G32B32A32_FLOAT, x fastest, as sbx_bake_noise_volume_host / ddsvolgen produce; only .r is read.
+ * The library keeps its own device copies (single channel, wrapped apron, TMA descriptors); the host arrays are consumed
+ * before the call returns. */
+int sbx_set_noise_volumes(sbx_ctx* ctx, const float* host_rgba_a, const float* host_rgba_b, int size);
+
 /* Options: "tail_waves_x100" T (default 0 = off) / "tail_max_waves_x100" M: with the default variant of an app that
  * ships a hybrid image, a launch smaller than M/100 waves of resident warps marches its last T/100 waves' worth of
  * rows with 4 lanes per pixel and the rest with one (measured on B200: it does not beat the whole-launch choice

@@ -132,3 +132,26 @@ def ref_dds_header(size):
     if n <= 0:
         raise RuntimeError("sbxref_dds_header failed: %d" % n)
     return buf.raw[:n]
+
+
+def oracle_set_noise_volumes(vol_a, vol_b):
+    """The two size^3 RGBA32F noise textures of the USE_NOISE_TEX cloud path (kept alive by the caller)."""
+    lib = _load(ORACLE_SO)
+    a = np.ascontiguousarray(vol_a, dtype=np.float32)
+    b = np.ascontiguousarray(vol_b, dtype=np.float32)
+    assert a.shape == b.shape and a.ndim == 4 and a.shape[0] == a.shape[1] == a.shape[2] and a.shape[3] == 4
+    lib.sbxoracle_set_noise_volumes.restype = C.c_int
+    lib.sbxoracle_set_noise_volumes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    rc = lib.sbxoracle_set_noise_volumes(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), int(a.shape[0]))
+    if rc != 0:
+        raise RuntimeError("sbxoracle_set_noise_volumes failed: %d" % rc)
+    _cache["noise_volumes"] = (a, b)      # the C side keeps the pointers
+    return a, b
+
+
+def oracle_sample_noise(which, x, y, z):
+    """One sample of noise texture `which` through the C restatement's sampler."""
+    lib = _load(ORACLE_SO)
+    lib.sbxoracle_sample_noise.restype = C.c_float
+    lib.sbxoracle_sample_noise.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
+    return np.float32(lib.sbxoracle_sample_noise(int(which), float(x), float(y), float(z)))

@@ -307,6 +307,123 @@ static void clouds_pixel(const uniforms_t* u, float fx, float fy, float out[4]) 
     main_image(u, clouds_render, eye, look_at, 1.0f, fx, fy, out);   /* FOV 1. (:220) */
 }
 
+/* ========================= APP_CLOUDS with USE_NOISE_TEX (src/app_clouds.h:8-9) ================ *
+ * The HLSL-only branch of the cloud app: the density comes from two 3-D noise textures (u_tex_noise, u_tex_noise_2:
+ * :51-55) sampled with u_sampler0 -- D3D11_FILTER_MIN_MAG_MIP_LINEAR, WRAP addressing on u, v and w
+ * (util/hlsltoy/src/hlsltoy.cpp:244-249) -- at LOD 0 (`SampleLevel(u_sampler0, pos, 0).r`, :69, :77).
+ *
+ * PARITY UNPINNED: the reference has no C++ statement of that sampler (the C++ build cannot compile this branch), no
+ * texture files and no output images, and hardware filtering is only specified up to its fixed-point precision.  This
+ * restatement therefore DEFINES the sampler, following the D3D11.3 functional specification's description of linear
+ * filtering (7.18.8; D3D11_SUBTEXEL_FRACTIONAL_BIT_COUNT = 8):
+ *     per axis:  u' = u - floor(u)                        (WRAP)
+ *                t  = u' * N - 0.5                         (texel space, texel centres at i + 0.5)
+ *                i0 = floor(t),  f = t - i0,  i1 = i0 + 1  (both wrapped into [0, N))
+ *                w  = floor(f * 256 + 0.5) / 256           (8-bit sub-texel weight)
+ *     value = lerp_z(lerp_y(lerp_x(...)))  with lerp(a, b, w) = a * (1 - w) + b * w in fp32, x innermost
+ * Texels are the .r channel of size^3 R32G32B32A32_FLOAT volumes, x fastest (what ddsvolgen writes). */
+static const float* g_noise_vol[2];
+static int g_noise_size;
+int sbxoracle_set_noise_volumes(const float* rgba_a, const float* rgba_b, int size) {
+    if (!rgba_a || !rgba_b || size <= 0) return SBX_ERR_INVALID;
+    g_noise_vol[0] = rgba_a; g_noise_vol[1] = rgba_b; g_noise_size = size;
+    return SBX_OK;
+}
+typedef struct { int i0, i1; float w; } tex_axis;
+static tex_axis tex_coord(float u, int n) {
+    tex_axis a;
+    float uw = u - floorf(u);
+    float t = uw * (float)n - 0.5f;
+    float fl = floorf(t);
+    float f = t - fl;
+    int i0 = (int)fl;
+    a.w = floorf(f * 256.0f + 0.5f) / 256.0f;
+    a.i0 = ((i0 % n) + n) % n;
+    a.i1 = (a.i0 + 1) % n;
+    return a;
+}
+static float tex_lerp(float a, float b, float w) { return a * (1.0f - w) + b * w; }
+static float tex_sample_r(int which, v3 pos) {
+    const float* vol = g_noise_vol[which];
+    const int n = g_noise_size;
+    tex_axis x = tex_coord(pos.x, n), y = tex_coord(pos.y, n), z = tex_coord(pos.z, n);
+#define TEXEL(ix, iy, iz) vol[(((size_t)(iz) * n + (iy)) * n + (ix)) * 4]
+    float c00 = tex_lerp(TEXEL(x.i0, y.i0, z.i0), TEXEL(x.i1, y.i0, z.i0), x.w);
+    float c10 = tex_lerp(TEXEL(x.i0, y.i1, z.i0), TEXEL(x.i1, y.i1, z.i0), x.w);
+    float c01 = tex_lerp(TEXEL(x.i0, y.i0, z.i1), TEXEL(x.i1, y.i0, z.i1), x.w);
+    float c11 = tex_lerp(TEXEL(x.i0, y.i1, z.i1), TEXEL(x.i1, y.i1, z.i1), x.w);
+#undef TEXEL
+    return tex_lerp(tex_lerp(c00, c10, y.w), tex_lerp(c01, c11, y.w), z.w);
+}
+/* test hook: one sample of texture `which` at pos (the sampler rule above, as the frames use it) */
+float sbxoracle_sample_noise(int which, float x, float y, float z) {
+    if (which < 0 || which > 1 || !g_noise_vol[which]) return 0.0f;
+    return tex_sample_r(which, V3(x, y, z));
+}
+static float g_remap(float v, float omin, float omax, float nmin, float nmax) {   /* src/util.h:127-138 */
+    return nmin + (((v - omin) / (omax - omin)) * (nmax - nmin));
+}
+static float clouds_tex_density(const uniforms_t* u, v3 pos_in, float height) {   /* :62-86, USE_NOISE_TEX */
+    v3 pos = scale3(pos_in, .001f);
+    float shape = tex_sample_r(0, pos);
+    float w = tex_sample_r(1, pos);
+    float ww = w * (1.0f - height) + (1.0f - w) * height;            /* mix(w, 1. - w, height) */
+    shape = g_remap(shape, ww * .7f, 1.0f, 0.0f, 1.0f);
+    const float cov = 1.0f - u->p->cld_coverage;
+    return shape * g_smoothstep(cov, cov + .0135f, shape);
+}
+static float clouds_tex_illuminate(const uniforms_t* u, v3 origin, v3 V, v3 L) {   /* :91-123 */
+    const sbx_params* p = u->p;
+    const float dt = p->cld_thick / (float)p->cld_march_steps;
+    volume_t vol = construct_volume(origin);
+    vol.pos = add3(vol.pos, scale3(L, dt));
+    for (int i = 0; i < p->illum_march_steps; i++) {
+        vol.height = (float)i / (float)p->illum_march_steps;
+        float density = clouds_tex_density(u, vol.pos, vol.height);
+        vol.transmittance *= m_exp(-density * p->sigma_scattering * dt);
+        vol.pos = add3(vol.pos, scale3(L, dt));
+    }
+    return vol.transmittance * p->sun_power * hg_phase(g_clamp(dot3(L, V), 0.0f, 1.0f), .2f);
+}
+static v3 clouds_tex_render(const uniforms_t* u, ray_t eye, v3 point_cam) {       /* :153-218 */
+    (void)point_cam;
+    const sbx_params* p = u->p;
+    clouds_vecs cv = clouds_uniform_vecs(p);
+    v3 sky = clouds_sky(u, eye.direction);
+    if (dot3(eye.direction, V3(0, 1, 0)) < 0.05f) return sky;
+    v3 projection = divs3(eye.direction, eye.direction.y);
+    v3 origin = add3(eye.origin, scale3(projection, 150.0f));
+    origin = add3(origin, scale3(scale3(cv.wind_dir, u->time), 1.0f / .001f));
+    volume_t cloud = construct_volume(origin);
+    float t = 0.0f;
+    const float dt = p->cld_thick / (float)p->cld_march_steps;
+    for (int i = 0; i < p->cld_march_steps; i++) {
+        cloud.height = (float)i / (float)p->cld_march_steps;
+        cloud.pos = add3(cloud.origin, rscale3(t, projection));
+        t += dt;
+        float density = clouds_tex_density(u, cloud.pos, cloud.height);
+        if (!(density < .005f)) {                                    /* integrate_volume, :125-148 */
+            float T_i = m_exp(-density * p->sigma_scattering * dt);
+            cloud.transmittance *= T_i;
+            float add = (density * p->sigma_scattering) * clouds_tex_illuminate(u, cloud.pos, eye.direction, cv.sun_dir) *
+                        cloud.transmittance * dt;
+            cloud.radiance = adds3(cloud.radiance, add);
+            cloud.alpha += (1.0f - T_i) * (1.0f - cloud.alpha);
+        }
+        if (cloud.alpha > .999f) break;
+    }
+    float cutoff = dot3(eye.direction, V3(0, 1, 0));
+    float a = cloud.alpha * g_smoothstep(.0f, .2f, cutoff);
+    return abs3(mix3(sky, cloud.radiance, a));
+}
+static void clouds_tex_pixel(const uniforms_t* u, float fx, float fy, float out[4]) {
+    v3 eye = V3(0, -.5f, 0);
+    float angle = u->mouse[0] * .5f;
+    v3 look_at = mat_vec(rotate_around_y(angle), V3(0, 0, -1));
+    if (!g_noise_vol[0]) { out[0] = out[1] = out[2] = out[3] = 0.0f; return; }
+    main_image(u, clouds_tex_render, eye, look_at, 1.0f, fx, fy, out);
+}
+
 /* ============================== APP_ATMOSPHERE (src/app_atmosphere.h) ========================= */
 #define ATM_EARTH_RADIUS 6360e3f
 #define ATM_RADIUS 6420e3f
@@ -1315,6 +1432,7 @@ static int render_frame(pixel_fn fn, const sbx_params* p, const sbx_shard* shard
     }
 ORACLE_ENTRY(egg, egg_pixel)
 ORACLE_ENTRY(clouds, clouds_pixel)
+ORACLE_ENTRY(clouds_tex, clouds_tex_pixel)
 ORACLE_ENTRY(atmosphere, atmosphere_pixel)
 ORACLE_ENTRY(planet, planet_pixel)
 ORACLE_ENTRY(raytracer, raytracer_pixel)

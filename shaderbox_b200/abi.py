@@ -14,6 +14,7 @@ SBX_ERR_NOMEM = -6
 SBX_ERR_UNSUPPORTED = -7
 
 APPS = ("APP_EGG", "APP_CLOUDS", "APP_ATMOSPHERE", "APP_PLANET", "APP_RAYTRACER", "APP_SDF_AO", "APP_VINYL")
+# + "APP_CLOUDS_TEX": APP_CLOUDS with USE_NOISE_TEX (hand-written image only: the branch is HLSL in the reference)
 
 
 class Params(C.Structure):

@@ -89,6 +89,7 @@ sbx::driver_api* sbx::load_driver(std::string* err) {
     SBX_SYM(StreamWaitValue32, "cuStreamWaitValue32_v2")
     SBX_SYM(StreamWriteValue32, "cuStreamWriteValue32_v2")
     SBX_SYM(StreamBatchMemOp, "cuStreamBatchMemOp_v2")
+    SBX_SYM(TensorMapEncodeTiled, "cuTensorMapEncodeTiled")
     SBX_SYM(StreamWaitEvent, "cuStreamWaitEvent")
     SBX_SYM(StreamCreate, "cuStreamCreate")
     SBX_SYM(StreamDestroy, "cuStreamDestroy_v2")
@@ -112,6 +113,7 @@ struct kernel_image {
     int warps_per_cta = 4;
     int tile_w = SBX_TILE_W, tile_h = SBX_TILE_H, lanes_per_pixel = 1;   // sbx_image_info of the image
     int hybrid_lanes = 0;         // > 1: the image has a second region marched with this many lanes per pixel
+    int uses_noise_tex = 0;          // sbx_image_hints[1]: sbx_render takes a second parameter (sbx_tex_params)
     int trivial_rows_permille = 0;   // sbx_image_hints[0]: this share of the frame's bottom rows is trivial (issued last)
     std::string variant;
 };
@@ -157,6 +159,8 @@ struct sbx_ctx {
     int opt_record_events = 1;       // bracket every render launch with timing events (sbx_last_timing.kernel_ms)
     int opt_tail_waves_x100 = 0;     // hybrid image (opt-in): march the last this-many waves of the launch with 4 lanes per pixel
     int opt_tail_max_waves_x100 = 1200;  // ... for launches below this many waves (a long launch amortises its tail anyway)
+    CUdeviceptr noise_vol[2] = {0, 0};   // padded single-channel noise textures (sbx_set_noise_volumes)
+    sbx_tex_params tex{};
     CUdeviceptr trace = 0;           // profiling hook: per-warp records of the next launches (trace images only)
     CUdeviceptr done_counters = 0;   // ring of CTA counters for launches that signal a completion flag
     unsigned done_seq = 0;
@@ -276,8 +280,10 @@ int bind_image(sbx_ctx* ctx, const std::string& key, const std::string& cubin, c
         size_t bytes = 0;
         int v[4] = {0, 0, 0, 0};
         if (ctx->cu->ModuleGetGlobal(&hints, &bytes, img.module, "sbx_image_hints") == CUDA_SUCCESS && bytes >= sizeof v &&
-            ctx->cu->MemcpyDtoH(v, hints, sizeof v) == CUDA_SUCCESS && v[0] > 0 && v[0] < 1000)
-            img.trivial_rows_permille = v[0];
+            ctx->cu->MemcpyDtoH(v, hints, sizeof v) == CUDA_SUCCESS) {
+            if (v[0] > 0 && v[0] < 1000) img.trivial_rows_permille = v[0];
+            img.uses_noise_tex = v[1] == 1;
+        }
     }
     auto it = ctx->images.find(key);
     if (it != ctx->images.end() && it->second.module) ctx->cu->ModuleUnload(it->second.module);
@@ -414,6 +420,7 @@ void sbx_destroy(sbx_ctx* ctx) {
         for (CUevent e : ctx->times_ev) if (e) ctx->cu->EventDestroy(e);
         if (ctx->frame) ctx->cu->MemFree(ctx->frame);
         if (ctx->done_counters) ctx->cu->MemFree(ctx->done_counters);
+        for (CUdeviceptr v : ctx->noise_vol) if (v) ctx->cu->MemFree(v);
         if (ctx->ev0) ctx->cu->EventDestroy(ctx->ev0);
         if (ctx->ev1) ctx->cu->EventDestroy(ctx->ev1);
         if (ctx->ev2) ctx->cu->EventDestroy(ctx->ev2);
@@ -633,7 +640,9 @@ static int render_launch(sbx_ctx* ctx, const sbx_params* p, const launch_job& jo
     // a launch without pixels still publishes its completion flag (one idle CTA)
     if (warps == 0 && !job.done_flag) return SBX_OK;
     const unsigned grid = (unsigned)std::max<long long>(1, (warps + img->warps_per_cta - 1) / img->warps_per_cta);
-    void* args[] = {&L};
+    if (img->uses_noise_tex && !ctx->noise_vol[0])
+        return ctx->fail(SBX_ERR_INVALID, "%s samples the 3-D noise textures: call sbx_set_noise_volumes first", ctx->current_app.c_str());
+    void* args[] = {&L, &ctx->tex};   // (the second parameter exists only in images that declare it)
     // the two timing events cost ~2 us of stream time each: a caller that times its own launches switches them off
     const bool timed = ctx->opt_record_events || !job.out_is_frame;
     if (timed) SBX_TRY(ctx->cu->EventRecord(ctx->ev0, stream), "cuEventRecord");
@@ -775,6 +784,46 @@ int sbx_stream_wait_flags(sbx_ctx* ctx, const unsigned* dev_flags, int n, unsign
         ops[i].waitValue.flags = CU_STREAM_WAIT_VALUE_GEQ;
     }
     SBX_TRY(ctx->cu->StreamBatchMemOp((CUstream)stream, (unsigned)n, ops, 0), "cuStreamBatchMemOp(wait flags)");
+    return SBX_OK;
+}
+
+int sbx_set_noise_volumes(sbx_ctx* ctx, const float* host_rgba_a, const float* host_rgba_b, int size) {
+    if (!ctx || !host_rgba_a || !host_rgba_b || size < 2 || size > 1024) return SBX_ERR_INVALID;
+    ctx_scope scope(ctx);
+    const int padded = size + 2;
+    const int pitch_x = (padded + 3) / 4 * 4;                   // rows of whole 16-byte units (TMA strides)
+    const size_t floats = (size_t)pitch_x * padded * padded;
+    std::vector<float> staging(floats);
+    SBX_TRY(ctx->cu->StreamSynchronize(nullptr), "cuStreamSynchronize");
+    const float* src[2] = {host_rgba_a, host_rgba_b};
+    for (int t = 0; t < 2; ++t) {
+        // the .r channel with a one-texel apron of wrapped neighbours: padded[k] = texel[(k - 1) mod size]
+        std::fill(staging.begin(), staging.end(), 0.0f);
+        for (int z = 0; z < padded; ++z)
+            for (int y = 0; y < padded; ++y) {
+                const size_t sz = (size_t)((z - 1 + size) % size), sy = (size_t)((y - 1 + size) % size);
+                float* row = staging.data() + ((size_t)z * padded + y) * pitch_x;
+                for (int x = 0; x < padded; ++x) row[x] = src[t][((sz * size + sy) * size + (size_t)((x - 1 + size) % size)) * 4];
+            }
+        if (ctx->noise_vol[t]) { ctx->cu->MemFree(ctx->noise_vol[t]); ctx->noise_vol[t] = 0; }
+        if (ctx->cu->MemAlloc(&ctx->noise_vol[t], floats * sizeof(float)) != CUDA_SUCCESS) return ctx->fail(SBX_ERR_NOMEM, "cuMemAlloc(noise volume) failed");
+        SBX_TRY(ctx->cu->MemcpyHtoD(ctx->noise_vol[t], staging.data(), floats * sizeof(float)), "cuMemcpyHtoD(noise volume)");
+        // TMA descriptor: rank 3 fp32, x fastest, 8 x 4 x 4 boxes (x starts on 16-byte boundaries), no swizzle, zero fill outside
+        CUtensorMap map;
+        const cuuint64_t dims[3] = {(cuuint64_t)padded, (cuuint64_t)padded, (cuuint64_t)padded};
+        const cuuint64_t strides[2] = {(cuuint64_t)pitch_x * sizeof(float), (cuuint64_t)pitch_x * padded * sizeof(float)};
+        const cuuint32_t box[3] = {8, 4, 4}, elem[3] = {1, 1, 1};
+        SBX_TRY(ctx->cu->TensorMapEncodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)(uintptr_t)ctx->noise_vol[t], dims, strides, box, elem,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+                "cuTensorMapEncodeTiled");
+        static_assert(sizeof(CUtensorMap) == sizeof(ctx->tex.map[0]), "CUtensorMap is 128 bytes");
+        std::memcpy(ctx->tex.map[t], &map, sizeof map);     // travels as a __grid_constant__ kernel parameter
+        ctx->tex.vol[t] = (const float*)(uintptr_t)ctx->noise_vol[t];
+    }
+    ctx->tex.size = size;
+    ctx->tex.pitch_x = pitch_x;
+    ctx->tex.pitch_xy = pitch_x * padded;
     return SBX_OK;
 }
 

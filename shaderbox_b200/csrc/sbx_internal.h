@@ -54,6 +54,9 @@ struct driver_api {
     CUresult (*StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned);
     CUresult (*StreamWriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned);
     CUresult (*StreamBatchMemOp)(CUstream, unsigned, CUstreamBatchMemOpParams*, unsigned);
+    CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     CUresult (*StreamWaitEvent)(CUstream, CUevent, unsigned);
     CUresult (*StreamCreate)(CUstream*, unsigned);
     CUresult (*StreamDestroy)(CUstream);

@@ -76,6 +76,7 @@ def lib():
         L.sbx_multi_last_error.argtypes = [C.c_void_p]
         L.sbx_multi_last_error.restype = C.c_char_p
         L.sbx_set_trace_buffer.argtypes = [C.c_void_p, C.c_void_p]
+        L.sbx_set_noise_volumes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.sbx_frame_alloc.argtypes = [C.c_void_p, C.c_size_t, P(C.c_void_p)]
         L.sbx_frame_free.argtypes = [C.c_void_p, C.c_void_p]
         L.sbx_frame_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
@@ -106,7 +107,7 @@ EXPORTS = (
     "sbx_render_frame_part", "sbx_stream_wait_flags", "sbx_host_alloc", "sbx_host_free",
     "sbx_multi_create", "sbx_multi_destroy", "sbx_multi_gpus", "sbx_multi_ctx", "sbx_multi_load_app", "sbx_multi_set_option",
     "sbx_multi_render_device", "sbx_multi_render_host", "sbx_multi_stream", "sbx_multi_sync", "sbx_multi_last_timing",
-    "sbx_multi_last_error", "sbx_device_count", "sbx_set_trace_buffer", "sbx_stream_write_flag",
+    "sbx_multi_last_error", "sbx_device_count", "sbx_set_trace_buffer", "sbx_stream_write_flag", "sbx_set_noise_volumes",
 )
 
 
@@ -247,6 +248,14 @@ class Renderer:
         """Stream-ordered wait (on the device) until each of the n 32-bit flags at `dev_flags_ptr` is >= value."""
         self._check(self._L.sbx_stream_wait_flags(self._ctx, C.c_void_p(dev_flags_ptr), int(n), int(value), C.c_void_p(stream)),
                     "sbx_stream_wait_flags")
+
+    def set_noise_volumes(self, vol_a, vol_b):
+        """The two size^3 RGBA32F noise textures of APP_CLOUDS_TEX (the USE_NOISE_TEX cloud path); only .r is sampled."""
+        a = np.ascontiguousarray(vol_a, dtype=np.float32)
+        b = np.ascontiguousarray(vol_b, dtype=np.float32)
+        assert a.shape == b.shape and a.ndim == 4 and a.shape[0] == a.shape[1] == a.shape[2] and a.shape[3] == 4
+        self._check(self._L.sbx_set_noise_volumes(self._ctx, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), int(a.shape[0])),
+                    "sbx_set_noise_volumes")
 
     def set_trace_buffer(self, dev_ptr):
         self._check(self._L.sbx_set_trace_buffer(self._ctx, C.c_void_p(dev_ptr or None)), "sbx_set_trace_buffer")

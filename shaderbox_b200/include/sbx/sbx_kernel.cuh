@@ -52,11 +52,17 @@ extern "C" __device__ const int sbx_image_info[4] = {SBX_IMG_TILE_W, SBX_IMG_TIL
                                                      SBX_HYBRID_LANES > 1 ? SBX_HYBRID_LANES : 0};
 
 // read by the host at load time: { per-mille of the frame height, from the bottom, whose pixels are known to be trivial
-// (they return before any march) -- the launch issues those rows LAST; 0, 0, 0 }.  A scene kernel sets SBX_HINT_TRIVIAL_ROWS.
+// (they return before any march) -- the launch issues those rows LAST; 1 if the image needs the noise textures; 0, 0 }.  A scene kernel sets SBX_HINT_TRIVIAL_ROWS.
 #ifndef SBX_HINT_TRIVIAL_ROWS
 #define SBX_HINT_TRIVIAL_ROWS 0
 #endif
-extern "C" __device__ const int sbx_image_hints[4] = {SBX_HINT_TRIVIAL_ROWS, 0, 0, 0};
+extern "C" __device__ const int sbx_image_hints[4] = {SBX_HINT_TRIVIAL_ROWS,
+#ifdef SBX_USES_NOISE_TEX
+                                                      1,   // [1]: the kernel takes a second parameter, sbx_tex_params
+#else
+                                                      0,
+#endif
+                                                      0, 0};
 
 // ---- TMA bulk copy of the LUT block: global -> shared, completion on an mbarrier --------------
 __device__ __forceinline__ unsigned sbx_smem_addr(const void* p) {
@@ -108,15 +114,20 @@ struct sbx_app {
     float iGlobalTime;
     vec4 iMouse;
     bool sbx_coop;                          // this warp marches with several lanes per pixel (warp-uniform)
+    const sbx_tex_params* __restrict__ sbx_T;   // the 3-D noise textures (images built with -DSBX_USES_NOISE_TEX), else NULL
+    unsigned sbx_lanes;                     // the lanes of this warp that render a pixel (ballot taken with all 32 present)
 
 #include SBX_APP_HEADER
 
-    __device__ __forceinline__ explicit sbx_app(const sbx_launch* L, bool coop = false)
+    __device__ __forceinline__ explicit sbx_app(const sbx_launch* L, bool coop = false, const sbx_tex_params* T = nullptr,
+                                                unsigned lanes = 0xffffffffu)
         : sbx_L(L),
           iResolution(float(L->p.width), float(L->p.height)),
           iGlobalTime(sbx_param_time(L)),
           iMouse(sbx_param_mouse(L)),
-          sbx_coop(coop) {}
+          sbx_coop(coop),
+          sbx_T(T),
+          sbx_lanes(lanes) {}
 };
 
 }  // namespace sbx_glsl
@@ -160,8 +171,15 @@ __device__ __forceinline__ void sbx_prefetch_tables(const sbx_launch& L) {
 #endif
 }
 
+#ifdef SBX_USES_NOISE_TEX
+#define SBX_TEX_PARAM , const __grid_constant__ sbx_tex_params T
+#define SBX_TEX_ARG &T
+#else
+#define SBX_TEX_PARAM
+#define SBX_TEX_ARG nullptr
+#endif
 extern "C" __global__ void __launch_bounds__(SBX_WARPS_PER_CTA * 32, SBX_MIN_CTAS_PER_SM)
-sbx_render(const __grid_constant__ sbx_launch L) {
+sbx_render(const __grid_constant__ sbx_launch L SBX_TEX_PARAM) {
     sbx_prefetch_tables(L);
     sbx_stage_lut(L.lut);
 
@@ -217,11 +235,12 @@ sbx_render(const __grid_constant__ sbx_launch L) {
         lr = lr < L.local_rows ? lr : L.local_rows - 1;
     }
 
+    const unsigned lanes = __ballot_sync(0xffffffffu, valid || P > 1);   // who enters the pixel body (all 32 lanes vote here)
     if (valid || P > 1) {
         // local (compacted) row -> frame row of this shard
         const int y = L.n_parts == 1 ? lr : ((lr / L.stripe_rows) * L.n_parts + L.part) * L.stripe_rows + lr % L.stripe_rows;
 
-        sbx_glsl::sbx_app app(&L, coop);
+        sbx_glsl::sbx_app app(&L, coop, SBX_TEX_ARG, lanes);
         sbx_glsl::vec4 c;
         app.mainImage(c, sbx_glsl::vec2(float(x) + 0.5f, float(y) + 0.5f));
 

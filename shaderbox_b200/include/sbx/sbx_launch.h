@@ -56,4 +56,21 @@ typedef struct sbx_launch {
     unsigned long long* trace;
 } sbx_launch;
 
+/* Second kernel parameter of images built with -DSBX_USES_NOISE_TEX (the USE_NOISE_TEX cloud path, src/app_clouds.h:8-9,
+ * 51-55): the two 3-D noise textures.  Device layout (sbx_set_noise_volumes): the .r channel only, fp32, with a one-texel
+ * apron on every side that holds the WRAPPED neighbours (padded[k] = texel[(k - 1) mod size], k = 0 .. size + 1), so the
+ * sampler never wraps an index; rows are `pitch_x` floats long (a multiple of 4: TMA wants 16-byte strides).
+ * map[t] is the TMA descriptor of texture t (cuTensorMapEncodeTiled: rank 3, fp32, box 8 x 4 x 4, zero fill outside). */
+typedef struct sbx_tex_params {
+#if defined(__cplusplus)
+    alignas(64)
+#endif
+    unsigned long long map[2][16];   /* two CUtensorMap (128 bytes each, 64-byte aligned), read from the kernel's parameter space */
+    const float* vol[2];             /* padded volumes in global memory */
+    int size;                        /* texels per axis (N); the padded volume is (N + 2)^3 */
+    int pitch_x;                     /* floats per padded row */
+    int pitch_xy;                    /* floats per padded plane = pitch_x * (N + 2) */
+    int reserved;
+} sbx_tex_params;
+
 #endif

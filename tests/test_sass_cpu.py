@@ -67,3 +67,17 @@ def test_no_legacy_tensor_or_compat_paths():
     for image in os.listdir(IMAGES):
         o = set(ops(sass(image)))
         assert not (o & {"HMMA", "IMMA", "HGMMA"}), image                  # no dense contraction on this path: no tensor-core code
+
+
+def test_noise_texture_image_stages_tiles_with_tma_tensor_loads():
+    """APP_CLOUDS_TEX (USE_NOISE_TEX): the per-warp 4x4x4 texel boxes arrive by cp.async.bulk.tensor.3d (UTMALDG.3D) on the
+    warp's mbarrier; the box the lanes share is found with warp reductions (CREDUX min/max)."""
+    lines = sass("APP_CLOUDS_TEX.native.cubin")
+    o = ops(lines)
+    assert sum(1 for l in lines if l.startswith("UTMALDG.3D")) >= 2       # one load per texture
+    assert "SYNCS" in o and "CREDUX" in o and "LDS" in o
+
+
+def test_every_image_prefetches_the_memo_table_into_l2():
+    for image in ("APP_CLOUDS.native.cubin", "APP_CLOUDS.coop.cubin", "APP_PLANET.native.cubin"):
+        assert "UBLKPF" in ops(sass(image)), image                        # cp.async.bulk.prefetch.L2
