@@ -274,9 +274,9 @@ class Job:
         ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(steps)]
         env.barrier()
         for k in range(steps):
-            env.flush.zero_()                          # evict the previous frame (and the memo table) from L2, untimed
             if env.world > 1:
-                dist.barrier()                         # all ranks start the step together
+                dist.barrier()                         # all ranks start the step together ...
+            env.flush.zero_()                          # ... with the previous frame (and the memo table) evicted from L2; untimed
             ev[k][0].record(self.stream)
             self.launch()
             ev[k][1].record(self.stream)
@@ -492,7 +492,7 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s %dx%d u_time=%g %s" % (job.app, w, h, job.t, json.dumps(job.ov)), "variant": tm_variant(job.r, args),
                        "format": "RGBA32F", "frames_per_step": 1,
-                       "l2": "flushed between steps (256 MiB memset on the same stream, outside the timed events); the frame is write-only",
+                       "l2": "flushed before every step (256 MiB memset on the same stream, after the per-step barrier, outside the timed events); the frame is write-only",
                        "sharding": "none" if world == 1 else (
                            "%s; every rank's render kernel stores its pixels into rank 0's frame over NVLink (CUDA-IPC peer mapping); %s; "
                            "all inside the step" % (split_text, signal_text)),

@@ -22,11 +22,9 @@ PY
 }
 run n8 8
 run n8_nccl 8 --completion nccl --no-extra --no-group
-run n8_kernelflag 8 --completion kernel --no-extra --no-group
 run n4 4
 run n2 2 --no-extra
 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu --no-extra 2> $OUT/n1.err > $OUT/n1.json; python -c "
 import json; d=json.load(open('$OUT/n1.json')); print('n1: value %.1f ms/step %.4f e2e %.1f pageable %.1f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['pageable_value']))"
 for g in 1 2 4 8; do shaderbox_b200/sbx_cli render APP_CLOUDS 1920 1080 1.5 - --steps 128 --frames 10 --gpus $g; done 2>&1 | tee $OUT/cli.txt
-python tools/pcie_ceiling.py 512 2>&1 | tee $OUT/pcie_ceiling.txt
 echo done
