@@ -226,7 +226,8 @@ int sbx_frame_read(sbx_ctx* ctx, const float* dev, float* host, size_t bytes, vo
  *                            sbx_multi_sync().  *dev_frame_out stays owned by the group.
  *   sbx_multi_render_host    synchronous.  A frame from sbx_host_alloc is written by every GPU over its own PCIe link
  *                            (no gather, no copy); any other host frame is rendered on the device path and copied.
- * Frames are bit-identical to sbx_render_host on one GPU.  sbx_multi_ctx(i) exposes the i-th per-GPU context
+ * Frames are bit-identical to sbx_render_host on one GPU.  Calls on one group are serialised by the caller (like calls on
+ * one context).  sbx_multi_ctx(i) exposes the i-th per-GPU context
  * (options, timing).  sbx_multi_last_timing: kernel_ms of each GPU's last launch (after a sync / host render). */
 typedef struct sbx_multi sbx_multi;
 int sbx_multi_create(const int* devices_or_null, int n_gpus, sbx_multi** out);

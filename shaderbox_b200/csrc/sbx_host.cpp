@@ -55,6 +55,7 @@ sbx::driver_api* sbx::load_driver(std::string* err) {
     SBX_SYM(DevicePrimaryCtxRelease, "cuDevicePrimaryCtxRelease_v2")
     SBX_SYM(CtxPushCurrent, "cuCtxPushCurrent_v2")
     SBX_SYM(CtxPopCurrent, "cuCtxPopCurrent_v2")
+    SBX_SYM(CtxSynchronize, "cuCtxSynchronize")
     SBX_SYM(ModuleLoadData, "cuModuleLoadData")
     SBX_SYM(ModuleUnload, "cuModuleUnload")
     SBX_SYM(ModuleGetFunction, "cuModuleGetFunction")
@@ -794,7 +795,7 @@ int sbx_set_noise_volumes(sbx_ctx* ctx, const float* host_rgba_a, const float* h
     const int pitch_x = (padded + 3) / 4 * 4;                   // rows of whole 16-byte units (TMA strides)
     const size_t floats = (size_t)pitch_x * padded * padded;
     std::vector<float> staging(floats);
-    SBX_TRY(ctx->cu->StreamSynchronize(nullptr), "cuStreamSynchronize");
+    SBX_TRY(ctx->cu->CtxSynchronize(), "cuCtxSynchronize");   // launches still sampling the old volumes, on any stream
     const float* src[2] = {host_rgba_a, host_rgba_b};
     for (int t = 0; t < 2; ++t) {
         // the .r channel with a one-texel apron of wrapped neighbours: padded[k] = texel[(k - 1) mod size]

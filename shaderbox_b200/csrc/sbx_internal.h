@@ -19,6 +19,7 @@ struct driver_api {
     CUresult (*DevicePrimaryCtxRelease)(CUdevice);
     CUresult (*CtxPushCurrent)(CUcontext);
     CUresult (*CtxPopCurrent)(CUcontext*);
+    CUresult (*CtxSynchronize)(void);
     CUresult (*ModuleLoadData)(CUmodule*, const void*);
     CUresult (*ModuleUnload)(CUmodule);
     CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
