@@ -341,36 +341,60 @@ template <bool BOUNDED> SBX_FN vec4 render_clouds_coop(_in(ray_t) eye, bool acti
     float t = 0.0f;                                    // the reference's t of step `phase`: 0 (+ dt) (+ dt) ...
     for (int q = 0; q < phase; ++q) t += dt;
     bool done = !active;
-    for (int r = __all_sync(0xffffffffu, done) ? steps : 0; r * P < steps; ++r) {   // (a warp of rays below the horizon marches nothing)
-        const int i = r * P + phase;
-        float T_i = 1.0f, A = 0.0f;
-        bool hit = false;                              // this lane's step met cloud (integrate_volume's density test, :132)
-        if (!done && i < steps) {
-            const float2 pos_xy = pk_add(origin_xy, pk_mul(proj_xy, t));
-            const float pos_z = origin.z + t * projection.z;
-            const float density = density_view(pos_xy, pos_z);
-            if (!(density < .005f)) {
-                hit = true;
-                T_i = sbx_beer_lambert<BOUNDED>(density, dt);
-                A = (density * sigma_scattering) * illuminate_volume<BOUNDED>(pos_xy, pos_z, sun_dir);
+    // A round = U sub-rounds of P consecutive steps (lane `phase` takes step (r*U + h)*P + phase in sub-round h), evaluated
+    // back to back, then ONE vote and one in-order merge of the round's U*P steps; steps evaluated past the alpha exit are
+    // discarded (at most U*P - 1 of them per ray).  U = 2 halves the votes per step but measured 5 % SLOWER than U = 1
+    // (one rank's share at 8 GPUs 0.358 vs 0.342 ms, full frame 2.635 vs 2.504 ms; profiles/r02o_*): U stays 1.
+#ifndef SBX_COOP_UNROLL
+#define SBX_COOP_UNROLL 1
+#endif
+    const int U = SBX_COOP_UNROLL;
+    for (int r = __all_sync(0xffffffffu, done) ? steps : 0; r * P * U < steps; ++r) {   // (a warp of rays below the horizon marches nothing)
+        float T_h[U], A_h[U];
+        unsigned hits_h[U];
+        bool any_hit = false;
+#pragma unroll
+        for (int h = 0; h < U; ++h) { T_h[h] = 1.0f; A_h[h] = 0.0f; }
+#pragma unroll 1
+        for (int h = 0; h < U; ++h) {
+            const int i = (r * U + h) * P + phase;
+            float T_i = 1.0f, A = 0.0f;
+            bool hit = false;                          // this lane's step met cloud (integrate_volume's density test, :132)
+            if (!done && i < steps) {
+                const float2 pos_xy = pk_add(origin_xy, pk_mul(proj_xy, t));
+                const float pos_z = origin.z + t * projection.z;
+                const float density = density_view(pos_xy, pos_z);
+                if (!(density < .005f)) {
+                    hit = true;
+                    T_i = sbx_beer_lambert<BOUNDED>(density, dt);
+                    A = (density * sigma_scattering) * illuminate_volume<BOUNDED>(pos_xy, pos_z, sun_dir);
+                }
             }
+#pragma unroll
+            for (int q = 0; q < P; ++q) t += dt;       // this lane's next step is P steps on
+            any_hit = any_hit || hit;
+            const unsigned hits = hit ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < U; ++k)                // (a select per slot keeps T_h / A_h in registers under the rolled loop)
+                if (k == h) { T_h[k] = T_i; A_h[k] = A; hits_h[k] = hits; }
         }
+        if (__any_sync(0xffffffffu, any_hit)) {        // rounds in which no lane of the warp met cloud change nothing
 #pragma unroll
-        for (int q = 0; q < P; ++q) t += dt;           // this lane's next step is P steps on
-        const unsigned hits = __ballot_sync(0xffffffffu, hit) >> base;   // bit q: step r*P + q of this pixel integrates
-        if (__any_sync(0xffffffffu, hit)) {            // rounds in which no lane of the warp met cloud change nothing
+            for (int h = 0; h < U; ++h) {
+                const unsigned hits = __ballot_sync(0xffffffffu, hits_h[h] != 0u) >> base;   // bit q: step (r*U+h)*P + q integrates
 #pragma unroll
-            for (int q = 0; q < P; ++q) {              // steps r*P .. r*P+P-1 in order
-                const float Tq = __shfl_sync(0xffffffffu, T_i, base + q);
-                const float Aq = __shfl_sync(0xffffffffu, A, base + q);
-                // branch-free: a step that integrates nothing multiplies by 1 and adds +0, which change no bit of
-                // the accumulators whatever they hold (x * 1 == x; x + 0 == x for every x but -0, and none of them can
-                // be -0: they start at 1, +0, +0 and a sum only yields -0 from two -0 operands)
-                const bool use = !done && ((hits >> q) & 1u);
-                transmittance *= use ? Tq : 1.0f;
-                radiance += use ? Aq * transmittance * dt : 0.0f;
-                alpha += use ? (1.0f - Tq) * (1.0f - alpha) : 0.0f;
-                done = done || (use && alpha > .999f); // :197 (alpha only changes in a cloud step)
+                for (int q = 0; q < P; ++q) {          // the round's steps in order
+                    const float Tq = __shfl_sync(0xffffffffu, T_h[h], base + q);
+                    const float Aq = __shfl_sync(0xffffffffu, A_h[h], base + q);
+                    // branch-free: a step that integrates nothing multiplies by 1 and adds +0, which change no bit of
+                    // the accumulators whatever they hold (x * 1 == x; x + 0 == x for every x but -0, and none of them can
+                    // be -0: they start at 1, +0, +0 and a sum only yields -0 from two -0 operands)
+                    const bool use = !done && ((hits >> q) & 1u);
+                    transmittance *= use ? Tq : 1.0f;
+                    radiance += use ? Aq * transmittance * dt : 0.0f;
+                    alpha += use ? (1.0f - Tq) * (1.0f - alpha) : 0.0f;
+                    done = done || (use && alpha > .999f); // :197 (alpha only changes in a cloud step)
+                }
             }
             if (__all_sync(0xffffffffu, done)) break;  // `done` only changes in a merge: the exit vote is taken here alone
         }
