@@ -40,21 +40,8 @@ SBX_FN sbx_tex_stage* sbx_stage() {
     return &stages[threadIdx.x >> 5];
 }
 
-// one axis of the sampler (oracle tex_coord): padded index of the lower texel and the 8-bit weight
-SBX_FN void sbx_tex_axis(float u, float n, int& i0, float& w) {
-    const float uw = u - floor(u);            // WRAP
-    const float t = uw * n - 0.5f;            // texel space
-    const float fl = floor(t);
-    const float f = t - fl;
-    i0 = int(fl) + 1;                         // + 1: the apron
-    w = floor(f * 256.0f + 0.5f) / 256.0f;    // D3D11_SUBTEXEL_FRACTIONAL_BIT_COUNT = 8
-}
-SBX_FN float sbx_tex_lerp(float a, float b, float w) { return a * (1.0f - w) + b * w; }
-SBX_FN float sbx_tex_blend(const float* c, float wx, float wy, float wz) {   // c: x0y0z0 x1y0z0 x0y1z0 x1y1z0 x0y0z1 ...
-    const float c00 = sbx_tex_lerp(c[0], c[1], wx), c10 = sbx_tex_lerp(c[2], c[3], wx);
-    const float c01 = sbx_tex_lerp(c[4], c[5], wx), c11 = sbx_tex_lerp(c[6], c[7], wx);
-    return sbx_tex_lerp(sbx_tex_lerp(c00, c10, wy), sbx_tex_lerp(c01, c11, wy), wz);
-}
+// the sampler rule itself (sbx_tex_axis / sbx_tex_lerp / sbx_tex_blend) is the library's: hlsl_tex.h
+#include "hlsl_tex.h"
 
 // both textures at pos (already scaled by cld_noise_factor): .x = u_tex_noise.r, .y = u_tex_noise_2.r   (:69, :77).
 // WARP-COLLECTIVE: every lane of sbx_lanes calls it, in lock-step (the march loops below are written warp-uniform for

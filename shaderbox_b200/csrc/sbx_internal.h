@@ -72,6 +72,7 @@ driver_api* load_driver(std::string* err);   // NULL + *err when libcuda is miss
 CUcontext context_of(sbx_ctx* ctx);          // the primary context a sbx_ctx is bound to
 
 std::string suffix_float_literals(const std::string& src);
+std::string bind_hlsl_registers(const std::string& src);
 std::string library_dir();
 // NVRTC-compile an unchanged app header to an sm_100a cubin.  0 or SBX_ERR_*; log gets the compiler output.
 int compile_app_header(const std::string& header_path, const std::string& app_name,

@@ -93,6 +93,57 @@ std::string suffix_float_literals(const std::string& src) {
     return out;
 }
 
+// HLSL register bindings: `Type name : register(t1);` becomes `Type name = sbx_hlsl_bind(sbx_T, 1, (const Type*)0);`
+// (hlsl_tex.h).  Only the USE_NOISE_TEX branch of src/app_clouds.h (:51-55) has them; for every other header this is
+// the identity.  Works on the declaration as a whole, so comments and other uses of ':' are left alone.
+std::string bind_hlsl_registers(const std::string& src) {
+    std::string out;
+    out.reserve(src.size() + 256);
+    size_t i = 0;
+    const size_t n = src.size();
+    while (i < n) {
+        // try to match at i:  <ident> <ws> <ident> <ws>? ':' <ws>? "register" <ws>? '(' <letter><digits> ')' <ws>? ';'
+        size_t j = i;
+        auto skip_ws = [&](size_t k) { while (k < n && (src[k] == ' ' || src[k] == '\t')) ++k; return k; };
+        auto ident = [&](size_t k) { size_t e = k; while (e < n && is_ident(src[e])) ++e; return e; };
+        const bool at_ident_start = is_ident(src[i]) && !std::isdigit((unsigned char)src[i]) && (i == 0 || !is_ident(src[i - 1]));
+        if (at_ident_start) {
+            const size_t t_end = ident(j);
+            size_t k = skip_ws(t_end);
+            const size_t n_beg = k, n_end = ident(k);
+            k = skip_ws(n_end);
+            if (k > t_end && n_end > n_beg && k < n && src[k] == ':') {
+                k = skip_ws(k + 1);
+                if (src.compare(k, 8, "register") == 0) {
+                    k = skip_ws(k + 8);
+                    if (k < n && src[k] == '(') {
+                        k = skip_ws(k + 1);
+                        if (k < n && std::isalpha((unsigned char)src[k])) {
+                            size_t d = k + 1, d_end = d;
+                            while (d_end < n && std::isdigit((unsigned char)src[d_end])) ++d_end;
+                            size_t c = skip_ws(d_end);
+                            if (d_end > d && c < n && src[c] == ')') {
+                                c = skip_ws(c + 1);
+                                if (c < n && src[c] == ';') {
+                                    const std::string type = src.substr(i, t_end - i), name = src.substr(n_beg, n_end - n_beg);
+                                    out += type + " " + name + " = sbx_hlsl_bind(sbx_T, " + src.substr(d, d_end - d) + ", (const " + type + "*)0);";
+                                    i = c + 1;
+                                    continue;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            out.append(src, i, t_end - i);      // not a binding: copy the identifier and go on
+            i = t_end;
+            continue;
+        }
+        out += src[i++];
+    }
+    return out;
+}
+
 std::string library_dir() {
     Dl_info info;
     if (dladdr((void*)&library_dir, &info) && info.dli_fname) {
@@ -163,7 +214,7 @@ int compile_app_header(const std::string& header_path, const std::string& app_na
     nvrtc_api* rtc = load_nvrtc(&err);
     if (!rtc) { *log = err; return SBX_ERR_COMPILE; }
 
-    const std::string app_text = suffix_float_literals(text);
+    const std::string app_text = bind_hlsl_registers(suffix_float_literals(text));
     const std::string dir = library_dir();
     // translation unit: just the kernel header; the app text is an in-memory header
     const char* tu = "#include \"sbx/sbx_kernel.cuh\"\n";

@@ -45,3 +45,8 @@ struct hit_t {
 };
 #define max_dist 1e8f
 const hit_t no_hit = hit_t{float(max_dist + 1e1f), -1, vec3(0.0f, 0.0f, 0.0f), vec3(0.0f, 0.0f, 0.0f)};
+
+// HLSL resource types of the USE_NOISE_TEX branch (src/app_clouds.h:51-55), for app headers compiled with that define
+#if defined(USE_NOISE_TEX) && !defined(SBX_NATIVE_NOISE_TEX)
+#include "hlsl_tex.h"
+#endif

@@ -182,6 +182,41 @@ def test_prebuilt_kernel_images_are_sm100a_and_present():
         path = os.path.join(img_dir, app + ".plugin.cubin")
         assert os.path.exists(path), path + " missing: run __graft_entry__.build()"
     assert os.path.exists(os.path.join(img_dir, "sbx_util.cubin"))
+    # the USE_NOISE_TEX branch of the unchanged app_clouds.h (HLSL texture declarations rewritten at compile time) and its
+    # hand-written counterpart
+    for name in ("APP_CLOUDS_TEX.plugin.cubin", "APP_CLOUDS_TEX.tma.cubin"):
+        assert os.path.exists(os.path.join(img_dir, name)), name
+
+
+def test_hlsl_register_bindings_are_rewritten_only_where_they_occur(tmp_path):
+    """sbx_compile_app turns `Type name : register(tN);` into a bound member (include/sbx/hlsl_tex.h) and leaves every
+    other ':' alone: a header with a ternary, a label-like comment and a binding compiles; the same header with an
+    unknown resource type fails in the compiler, not in the rewrite."""
+    ok = tmp_path / "app_tex_probe.h"
+    ok.write_text('''#include "def.h"
+#include "util.h"
+Texture3D probe_tex : register(t2);
+SamplerState probe_sampler : register(s0);   // register(t9) in a comment : stays
+void setup_camera(_inout(vec3) eye, _inout(vec3) look_at) { eye = vec3(0, 0, 1); look_at = vec3(0, 0, 0); }
+void setup_scene() {}
+vec3 render(_in(ray_t) ray, _in(vec3) point_cam) {
+    float s = probe_tex.SampleLevel(probe_sampler, ray.direction, 0).r;
+    return point_cam.x > 0. ? vec3(s, s, s) : vec3(.5, .25, 0);
+}
+#define FOV 1.
+#include "main.h"
+''')
+    os.environ["SBX_COMPILE_DEFINES"] = "USE_NOISE_TEX=1;SBX_USES_NOISE_TEX=1"
+    try:
+        sbx.compile_app(str(ok), "APP_TEX_PROBE", str(tmp_path / "probe.cubin"))
+        assert os.path.getsize(tmp_path / "probe.cubin") > 1000
+        bad = tmp_path / "app_tex_bad.h"
+        bad.write_text(ok.read_text().replace("Texture3D probe_tex", "TextureCube probe_tex"))
+        with pytest.raises(sbx.SbxError) as e:
+            sbx.compile_app(str(bad), "APP_TEX_BAD", str(tmp_path / "bad.cubin"))
+        assert e.value.status == abi.SBX_ERR_COMPILE and "TextureCube" in str(e.value)
+    finally:
+        del os.environ["SBX_COMPILE_DEFINES"]
 
 
 def test_header_is_plain_c_and_links_from_c(tmp_path):

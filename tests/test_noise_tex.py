@@ -98,14 +98,17 @@ def test_noise_texture_clouds_match_the_oracle(size, w, h, t, ov):
     a, b = _volumes(size)
     loader.oracle_set_noise_volumes(a, b)
     want = loader.oracle_render("APP_CLOUDS_TEX", abi.default_params(w, h, t, **ov))
-    r = sbx.Renderer("APP_CLOUDS_TEX", device=0)
-    with pytest.raises(sbx.SbxError):
-        r.render(w, h, u_time=t, **ov)                         # no textures yet: refused, not rendered from garbage
-    r.set_noise_volumes(a, b)
-    got = r.render(w, h, u_time=t, **ov)
-    assert bits_equal(got, want), diff_report(got, want)
-    assert bits_equal(r.render(w, h, u_time=t, shard=(4, 3, 1), **ov), want[abi.shard_rows(4, 3, 1, h)])
-    r.close()
+    # "tma": the hand-written kernel (TMA-staged texel boxes);  "plugin" (= the default): the UNCHANGED src/app_clouds.h compiled with
+    # -DUSE_NOISE_TEX, its `Texture3D ... : register(tN)` declarations and SampleLevel calls resolved by include/sbx/hlsl_tex.h
+    for variant in ("tma", "plugin", None):
+        r = sbx.Renderer("APP_CLOUDS_TEX", device=0, variant=variant)
+        with pytest.raises(sbx.SbxError):
+            r.render(w, h, u_time=t, **ov)                     # no textures yet: refused, not rendered from garbage
+        r.set_noise_volumes(a, b)
+        got = r.render(w, h, u_time=t, **ov)
+        assert bits_equal(got, want), str(variant) + ": " + diff_report(got, want)
+        assert bits_equal(r.render(w, h, u_time=t, shard=(4, 3, 1), **ov), want[abi.shard_rows(4, 3, 1, h)])
+        r.close()
 
 
 @pytest.mark.gpu

@@ -72,7 +72,7 @@ def test_no_legacy_tensor_or_compat_paths():
 def test_noise_texture_image_stages_tiles_with_tma_tensor_loads():
     """APP_CLOUDS_TEX (USE_NOISE_TEX): the per-warp 4x4x4 texel boxes arrive by cp.async.bulk.tensor.3d (UTMALDG.3D) on the
     warp's mbarrier; the box the lanes share is found with warp reductions (CREDUX min/max)."""
-    lines = sass("APP_CLOUDS_TEX.native.cubin")
+    lines = sass("APP_CLOUDS_TEX.tma.cubin")
     o = ops(lines)
     assert sum(1 for l in lines if l.startswith("UTMALDG.3D")) >= 2       # one load per texture
     assert "SYNCS" in o and "CREDUX" in o and "LDS" in o
