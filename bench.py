@@ -458,14 +458,30 @@ def run_ours(args):
     e2e_s, e2e_sum, zero_copy = job.time_e2e(args.steps)
     e2e_page = job.time_e2e(args.steps, pageable=True) if world == 1 else None
 
+    # The side measurements must never cost the headline line: each runs under a watchdog; after the first failure (on
+    # any rank: a collective may be left half-done) the rest are skipped and the process exits without teardown.
     extras = {}
+    broken = None
     if not args.no_extra and args.workload == "clouds1080":
         for name in EXTRA_WORKLOADS:
-            extras[name] = extra_workload(env, name, args.extra_steps, args)
+            if broken:
+                extras[name] = {"skipped": "after " + broken}
+                continue
+            try:
+                with Watchdog(args.extra_timeout):
+                    extras[name] = extra_workload(env, name, args.extra_steps, args)
+            except BaseException as e:   # noqa: BLE001
+                broken = "%s: %r" % (name, e)
+                extras[name] = {"error": repr(e)}
 
     group_line = None
-    if world > 1 and not args.no_group:
-        group_line = single_process_group(env, job, args)
+    if world > 1 and not args.no_group and not broken:
+        try:
+            with Watchdog(args.extra_timeout):
+                group_line = single_process_group(env, job, args)
+        except BaseException as e:   # noqa: BLE001
+            broken = "single_process_group: %r" % (e,)
+            group_line = {"error": repr(e)}
 
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_src = peaks()
@@ -542,11 +558,38 @@ def run_ours(args):
                                       "stale": sha_now != sha_then, "image": image, "image_sha256": sha_now,
                                       "source": "ncu smsp__inst_executed.sum (profiles/traffic.json) / live kernel time; peak = 148 SMs x 4 schedulers x SM clock"}
         print(json.dumps(line), file=args.json_out, flush=True)
+    if broken:
+        sys.stderr.write("bench.py: a side measurement failed (%s); exiting without teardown\n" % broken)
+        sys.stderr.flush()
+        os._exit(0)
     job.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+class Watchdog:
+    """SIGALRM after `seconds`: turns a hang in a side measurement (a peer that died inside a collective) into an exception."""
+
+    def __init__(self, seconds):
+        self.seconds = int(seconds)
+
+    def __enter__(self):
+        import signal
+
+        def fire(signum, frame):
+            raise TimeoutError("no progress within %d s" % self.seconds)
+        self.old = signal.signal(signal.SIGALRM, fire)
+        signal.alarm(self.seconds)
+        return self
+
+    def __exit__(self, *exc):
+        import signal
+
+        signal.alarm(0)
+        signal.signal(signal.SIGALRM, self.old)
+        return False
 
 
 def single_process_group(env, job, args):
@@ -728,6 +771,7 @@ def main():
                          "thread block, waited for with cuStreamWaitValue32 -- or a 1-element NCCL all-reduce")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads (BASELINE configs 3-5)")
     ap.add_argument("--extra-steps", type=int, default=20)
+    ap.add_argument("--extra-timeout", type=int, default=90, help="watchdog (s) per side measurement")
     ap.add_argument("--no-group", action="store_true", help="N>1: skip the single-process sbx_multi_* measurement")
     ap.add_argument("--format", default="f32", choices=["f32", "rgba8"],
                     help="frame format: raw float4 (BASELINE.json) or the 8-bit swap-chain format of the reference's presenting hosts")
