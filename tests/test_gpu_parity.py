@@ -308,6 +308,8 @@ FULL = [
     ("APP_ATMOSPHERE", 1920, 1080, 1.0, {}, 4),
     ("APP_PLANET", 3840, 2160, 2.0, {}, 8),
     ("APP_RAYTRACER", 7680, 4320, 1.0, {}, 8),
+    ("APP_CLOUDS", 3840, 2160, 1.5, {"cld_march_steps": 128}, 8),        # the metric's scene on the larger frames north_star names
+    ("APP_CLOUDS", 7680, 4320, 1.5, {"cld_march_steps": 128}, 8),
 ]
 
 
