@@ -113,6 +113,7 @@ int dispatch(sbx_multi* m, const sbx_multi::task& t) {
     m->finished.store(0, std::memory_order_relaxed);
     if (m->n > 1) {
         m->go.fetch_add(1, std::memory_order_release);
+        { std::lock_guard<std::mutex> lk(m->m); }   // a worker between its predicate check and its wait holds m: no lost wake-up
         m->cv.notify_all();
     }
     m->status[0] = run_part(m, 0);
@@ -186,6 +187,7 @@ int sbx_multi_create(const int* devices, int n_gpus, sbx_multi** out) {
 void sbx_multi_destroy(sbx_multi* m) {
     if (!m) return;
     m->quit.store(true);
+    { std::lock_guard<std::mutex> lk(m->m); }
     m->cv.notify_all();
     for (auto& t : m->workers) t.join();
     for (int i = 0; i < (int)m->ctx.size(); ++i) {
