@@ -413,6 +413,12 @@ class MultiRenderer:
     def sync(self):
         self._check(self._L.sbx_multi_sync(self._m), "sbx_multi_sync")
 
+    def timing(self, i):
+        """sbx_last_timing of GPU i's context (launch shape, image, kernel time)."""
+        t = Timing()
+        self._check(self._L.sbx_last_timing(self._L.sbx_multi_ctx(self._m, int(i)), C.byref(t)), "sbx_last_timing")
+        return {k: getattr(t, k) for k, _ in Timing._fields_}
+
     def kernel_ms(self):
         n = len(self.devices)
         arr = (C.c_float * n)()
