@@ -129,6 +129,9 @@ int fake_cuda_get_launch(size_t i, fake_launch* out) {
 void fake_cuda_reset_log(void) { pthread_mutex_lock(&g_lock); g_log_len = 0; pthread_mutex_unlock(&g_lock); }
 long fake_cuda_live_allocs(void) { pthread_mutex_lock(&g_lock); long n = g_allocs; pthread_mutex_unlock(&g_lock); return n; }
 size_t fake_cuda_sizeof_launch(void) { return sizeof(fake_launch); }
+static int g_fail_launch_device = -1, g_fail_launch_count;
+/* the next `count` sbx_render launches on `device` fail with CUDA_ERROR_LAUNCH_FAILED */
+void fake_cuda_fail_launches(int device, int count) { pthread_mutex_lock(&g_lock); g_fail_launch_device = device; g_fail_launch_count = count; pthread_mutex_unlock(&g_lock); }
 void fake_cuda_fail_alloc_at(long n) { pthread_mutex_lock(&g_lock); g_alloc_calls = 0; g_fail_alloc_at = n; pthread_mutex_unlock(&g_lock); }
 
 /* ---- init / devices / contexts ------------------------------------------------------------------------------- */
@@ -490,6 +493,11 @@ CUresult cuLaunchKernel(CUfunction fn, unsigned gx, unsigned gy, unsigned gz, un
     if (!f || t_depth <= 0) return CUDA_ERROR_INVALID_HANDLE;
     if (gx == 0 || gy == 0 || gz == 0 || bx * by * bz == 0 || bx * by * bz > (unsigned)f->max_threads || gy > 65535u || gz > 65535u)
         return CUDA_ERROR_INVALID_VALUE;
+    pthread_mutex_lock(&g_lock);
+    const int refuse = g_fail_launch_count > 0 && g_fail_launch_device == current_device() && !strcmp(f->name, "sbx_render");
+    if (refuse) g_fail_launch_count--;
+    pthread_mutex_unlock(&g_lock);
+    if (refuse) return CUDA_ERROR_LAUNCH_FAILED;
     fake_launch L;
     memset(&L, 0, sizeof L);
     snprintf(L.name, sizeof L.name, "%s", f->name);

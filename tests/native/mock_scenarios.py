@@ -354,6 +354,33 @@ def scenario_noise_tex():
     return report
 
 
+def scenario_multi_launch_failure():
+    """A launch that fails on one GPU of the group: the frame call reports which part failed, nothing hangs, and the group
+    renders the next frame normally."""
+    m = mock()
+    m.fake_cuda_fail_launches.argtypes = [C.c_int, C.c_int]
+    g = sbx.MultiRenderer("APP_CLOUDS", n_gpus=8)
+    p = abi.default_params(256, 144, 1.0)
+    ptr = g.host_alloc(256 * 144 * 16)
+    report = {}
+    for dev in (0, 5):
+        m.fake_cuda_fail_launches(dev, 1)
+        try:
+            g.render_host_ptr(p, ptr)
+            report[str(dev)] = "no error"
+        except sbx.SbxError as e:
+            report[str(dev)] = str(e)
+        m.fake_cuda_reset_log()
+        g.render_host_ptr(p, ptr)              # the next frame is complete again
+        assert m.fake_cuda_launch_count() == 8
+        g.render_device(p)
+        g.sync()
+    g.host_free(ptr)
+    g.close()
+    report["live_allocs_after_close"] = m.fake_cuda_live_allocs()
+    return report
+
+
 def scenario_wrong_device():
     """A GPU that is not sm_100 is refused at sbx_create (run with SBX_FAKE_CC_MAJOR=9)."""
     try:

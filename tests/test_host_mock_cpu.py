@@ -134,3 +134,33 @@ def test_worker_hand_off_under_thread_sanitizer(tmp_path):
     assert "ThreadSanitizer" not in r.stderr, r.stderr[-6000:]
     assert r.returncode == 0, r.stdout + r.stderr[-2000:]
     assert json.loads(r.stdout.strip().splitlines()[-1]) == {"ok": True, "gpus": 8, "frames": 3000}
+
+
+def test_cli_paths_under_the_mock(mock_dir, tmp_path):
+    """sbx_cli (the C++ launcher of INTEGRATION.md): every sub-path runs to completion and writes files of the right size."""
+    cli = os.path.join(ROOT, "shaderbox_b200", "sbx_cli")
+    env = dict(os.environ, LD_LIBRARY_PATH=mock_dir, SBX_FAKE_GPUS="8")
+
+    def run(*args):
+        return subprocess.run([cli, *args], env=env, capture_output=True, text=True, timeout=120)
+
+    out = str(tmp_path / "f.rgba32f")
+    r = run("render", "APP_CLOUDS", "640", "360", "1.5", out, "--steps", "128", "--gpus", "8")
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout)
+    assert line["gpus"] == 8 and os.path.getsize(out) == 640 * 360 * 16
+    r = run("render", "APP_EGG", "64", "36", "0", "-", "--ppm", str(tmp_path / "f.ppm"), "--rgba8", str(tmp_path / "f.rgba8"))
+    assert r.returncode == 0 and os.path.getsize(tmp_path / "f.rgba8") == 64 * 36 * 4
+    assert open(tmp_path / "f.ppm", "rb").read(15).startswith(b"P6\n64 36\n255\n")
+    r = run("render", "APP_PLANET", "64", "36", "0", out, "--frames", "3", "--variant", "plugin")
+    assert r.returncode == 0 and json.loads(r.stdout)["regs"] > 0
+    r = run("bake", "16", str(tmp_path / "v.dds"))
+    assert r.returncode == 0 and os.path.getsize(tmp_path / "v.dds") == 148 + 16 ** 3 * 16
+    assert run("render", "APP_CLOUDS", "0", "36", "0", out).returncode == 2
+    assert run("render", "APP_NOPE", "8", "8", "0", out).returncode == 1
+    assert run("render", "APP_CLOUDS", "8", "8", "0", out, "--device", "9").returncode == 1
+
+
+def test_a_failed_launch_on_one_gpu_of_the_group_is_reported_and_survivable(mock_dir):
+    rep = scenario(mock_dir, "multi_launch_failure", SBX_FAKE_GPUS=8)
+    assert "GPU part 0" in rep["0"] and "GPU part 5" in rep["5"] and rep["live_allocs_after_close"] == 0
