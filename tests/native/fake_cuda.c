@@ -51,6 +51,7 @@ typedef struct fake_module {
     size_t n_sym;
     const char* str;
     struct fake_global { char name[64]; void* mem; size_t bytes; struct fake_global* next; } * globals;
+    struct fake_function* functions;
 } fake_module;
 
 typedef struct fake_function {
@@ -58,6 +59,7 @@ typedef struct fake_function {
     char name[64];
     int regs, max_threads, n_params;
     unsigned param_size[FAKE_MAX_PARAMS];
+    struct fake_function* next;
 } fake_function;
 
 typedef struct fake_context { int device; int retained; } fake_context;
@@ -237,9 +239,10 @@ CUresult cuModuleLoadData(CUmodule* out, const void* image) {
 CUresult cuModuleUnload(CUmodule mod) {
     fake_module* m = (fake_module*)mod;
     if (!m) return CUDA_ERROR_INVALID_HANDLE;
-    for (struct fake_global* g = m->globals; g;) { struct fake_global* n = g->next; free(g->mem); free(g); g = n; }
+    for (struct fake_global* g = m->globals; g;) { struct fake_global* n = g->next; drop_range(g->mem, 1); free(g->mem); free(g); g = n; }
+    for (fake_function* f = m->functions; f;) { fake_function* n = f->next; free(f); f = n; }
     free(m->image);
-    free(m);   /* functions of the module are leaked on purpose: the host keeps their handles until it drops the image */
+    free(m);
     return CUDA_SUCCESS;
 }
 /* walk .nv.info-style records: { u8 format, u8 attribute, u16 size-or-value } [+ payload when format == 4] */
@@ -277,6 +280,8 @@ CUresult cuModuleGetFunction(CUfunction* out, CUmodule mod, const char* name) {
     snprintf(sec, sizeof sec, ".nv.info.%s", name);
     scan_info(m, find_section(m, ".nv.info"), index, f);
     scan_info(m, find_section(m, sec), index, f);
+    f->next = m->functions;
+    m->functions = f;
     *out = (CUfunction)f;
     return CUDA_SUCCESS;
 }

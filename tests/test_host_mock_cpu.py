@@ -112,28 +112,48 @@ def test_group_needs_a_peer_path(mock_dir):
     assert rep["status"] == -7 and rep["live_allocs"] == 0
 
 
+def _sanitized_tree(tmp_path, flags, programs):
+    """libsbx's sources, the mock driver and the given C hosts built with the sanitizer `flags` into tmp_path."""
+    probe = tmp_path / "probe.c"
+    probe.write_text("int main(void){return 0;}\n")
+    if subprocess.run(["gcc", *flags, str(probe), "-o", str(tmp_path / "probe")], capture_output=True).returncode != 0:
+        pytest.skip("this gcc has no runtime for " + " ".join(flags))
+    d = str(tmp_path)
+    build_mock(d, extra=flags)
+    os.symlink(os.path.join(ROOT, "shaderbox_b200", "images"), os.path.join(d, "images"))      # the library finds its images beside itself
+    os.symlink(os.path.join(ROOT, "shaderbox_b200", "include"), os.path.join(d, "include"))
+    subprocess.run(["g++", *flags, "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-tsan", *INCLUDES,
+                    *[os.path.join(CSRC, f) for f in ("sbx_host.cpp", "sbx_multi.cpp", "sbx_rtc.cpp")], "-o", os.path.join(d, "libsbx.so"), "-ldl", "-lpthread"],
+                   check=True)
+    for prog in programs:
+        subprocess.run(["gcc", *flags, "-O1", "-g", "-std=gnu99", "-Wall", "-Wextra", "-Werror", os.path.join(NATIVE, prog + ".c"), "-o", os.path.join(d, prog),
+                        "-L" + d, "-lsbx", "-Wl,-rpath," + d], check=True)
+    return d
+
+
 def test_worker_hand_off_under_thread_sanitizer(tmp_path):
     """libsbx's sources + the mock + tests/native/multi_stress.c, all built with -fsanitize=thread: 3000 frames over 8 mock
     GPUs (pinned, device and pageable destinations interleaved, workers put to sleep now and then) without a report."""
-    probe = tmp_path / "probe.c"
-    probe.write_text("int main(void){return 0;}\n")
-    if subprocess.run(["gcc", "-fsanitize=thread", str(probe), "-o", str(tmp_path / "probe")], capture_output=True).returncode != 0:
-        pytest.skip("this gcc has no ThreadSanitizer runtime")
-    d = str(tmp_path)
-    tsan = ["-fsanitize=thread"]
-    build_mock(d, extra=tsan)
-    os.symlink(os.path.join(ROOT, "shaderbox_b200", "images"), os.path.join(d, "images"))      # the library finds its images beside itself
-    os.symlink(os.path.join(ROOT, "shaderbox_b200", "include"), os.path.join(d, "include"))
-    subprocess.run(["g++", *tsan, "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-tsan", *INCLUDES,
-                    *[os.path.join(CSRC, f) for f in ("sbx_host.cpp", "sbx_multi.cpp", "sbx_rtc.cpp")], "-o", os.path.join(d, "libsbx.so"), "-ldl", "-lpthread"],
-                   check=True)
-    subprocess.run(["gcc", *tsan, "-O1", "-g", "-std=gnu99", "-Wall", "-Wextra", "-Werror", os.path.join(NATIVE, "multi_stress.c"), "-o", os.path.join(d, "multi_stress"),
-                    "-L" + d, "-lsbx", "-Wl,-rpath," + d], check=True)
+    d = _sanitized_tree(tmp_path, ["-fsanitize=thread"], ["multi_stress"])
     env = dict(os.environ, LD_LIBRARY_PATH=d, SBX_FAKE_GPUS="8", TSAN_OPTIONS="exitcode=66 halt_on_error=0")
     r = subprocess.run([os.path.join(d, "multi_stress"), "8", "3000"], env=env, capture_output=True, text=True, timeout=600, cwd=d)
     assert "ThreadSanitizer" not in r.stderr, r.stderr[-6000:]
     assert r.returncode == 0, r.stdout + r.stderr[-2000:]
     assert json.loads(r.stdout.strip().splitlines()[-1]) == {"ok": True, "gpus": 8, "frames": 3000}
+
+
+def test_every_entry_point_under_address_and_ub_sanitizers(tmp_path):
+    """tests/native/abi_tour.c calls the whole single-GPU ABI (all 7 apps x native / plugin images, every output flavour,
+    parts + flags, host frames, IPC, options, noise volumes, the textured cloud images), multi_stress.c the group.  With
+    the mock, device memory is host memory of exactly the requested size: a copy with a wrong size or offset, a leak or
+    an undefined shift in the host library is a sanitizer report."""
+    d = _sanitized_tree(tmp_path, ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"], ["abi_tour", "multi_stress"])
+    env = dict(os.environ, LD_LIBRARY_PATH=d, SBX_FAKE_GPUS="8", ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="print_stacktrace=1")
+    for cmd in (["abi_tour"], ["multi_stress", "8", "600"]):
+        r = subprocess.run([os.path.join(d, cmd[0]), *cmd[1:]], env=env, capture_output=True, text=True, timeout=600, cwd=d)
+        assert "Sanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-6000:]
+        assert r.returncode == 0, r.stdout + r.stderr[-2000:]
+        assert json.loads(r.stdout.strip().splitlines()[-1])["ok"] is True
 
 
 def test_cli_paths_under_the_mock(mock_dir, tmp_path):
